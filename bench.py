@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - the mini-batch data path of BASELINE.json on B200.
+
+A step = one mini-batch: multi-hop fan-out sampling (+ relabel) of `--batch` seeds and the feature
+extract of the input frontier, on synthetic graphs of the named shapes (dist-gnn_b200/dgs_synth.py).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        this repo (sm_100a kernels)
+  python bench.py --impl reference ...                       CPU baseline arm (DGL-semantics
+                                                             sample_neighbors + index_select port,
+                                                             oracle/dgs_oracle.c, all host threads)
+
+N = 1  : BASELINE configs[1] - products-shaped graph resident in HBM, uniform [15,10,5], batch
+         1024, un-cached path (CSRSampler + _CAPI_cuda_index_select).
+N > 1  : the same shape sharded over the N GPUs of the box (node n lives on GPU n mod N: CSR rows
+         and feature rows), every rank samples its own seed batches through P2PCacheSampler /
+         P2PCacheFeatureServer; remote rows are NVLink peer loads issued inside the kernels, no
+         collective on the data path ("scaling": "weak").
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dist-gnn_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "sampled_edges_per_sec"
+UNIT = "edges/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default="products", choices=["tiny", "small", "products"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--fan-out", default="15,10,5")
+    ap.add_argument("--bias", action="store_true")
+    ap.add_argument("--extract-algo", type=int, default=0)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(args, fan_out):
+    import dgs_synth
+    N, E, D, dt = dgs_synth.SHAPES[args.shape]
+    return (f"{args.shape}-shaped synthetic graph ({N} nodes, ~{E} edges, {D}-dim "
+            f"{str(dt).replace('torch.', '')} feats), {'biased' if args.bias else 'uniform'} fan-out "
+            f"{fan_out}, batch {args.batch}")
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def cpu_baseline(args, fan_out, host_graph, seconds, steps=None, warmup=2):
+    """DGL-semantics CPU sample_neighbors + relabel + index_select (oracle port), all host threads."""
+    import numpy as np
+    import oracle
+    import dgs_synth
+    indptr, indices, probs, feat = host_graph
+    N = len(indptr) - 1
+    runner = oracle.CpuBatchRunner(indptr, indices, probs, feat, args.batch, fan_out)
+    nb = (steps or 200) + warmup
+    seeds = dgs_synth.seed_batches(N, args.batch, nb, seed=99).numpy()
+    for w in range(warmup):
+        runner.run(seeds[w], w)
+    edges = rows = done = 0
+    t0 = time.perf_counter()
+    while True:
+        e, r = runner.run(seeds[warmup + done], 1000 + done)
+        edges += e
+        rows += r
+        done += 1
+        el = time.perf_counter() - t0
+        if steps is not None:
+            if done >= steps:
+                break
+        elif el >= seconds or done >= 200:
+            break
+    row_bytes = feat.dtype.itemsize * feat.shape[1]
+    return {"value": edges / el, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"{done} batches of the same workload ({el:.1f} s), DGL-semantics "
+                      "sample_neighbors + to_block relabel + index_select restated in C/OpenMP "
+                      "(DGL itself is not installed)",
+            "batches_per_sec": done / el, "extract_gbps": rows * (2 * row_bytes + 8) / el / 1e9,
+            "ms_per_step": el / done * 1e3, "steps": done}
+
+
+def host_graph_from(args, device):
+    """Generate the graph once (on the GPU when there is one) and hand numpy copies to the CPU arm."""
+    import dgs_synth
+    N, E, D, dt = dgs_synth.SHAPES[args.shape]
+    indptr, indices, probs = dgs_synth.make_csr(N, E, seed=0, device=device, weights=args.bias)
+    feat = dgs_synth.make_features(N, D, dt, seed=0, device=device)
+    return indptr, indices, probs, feat
+
+
+def run_reference(args, fan_out):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    ip, ix, pr, ft = host_graph_from(args, dev)
+    host = (ip.cpu().numpy(), ix.cpu().numpy(), pr.cpu().numpy() if pr is not None else None,
+            ft.cpu().numpy())
+    del ip, ix, pr, ft
+    cb = cpu_baseline(args, fan_out, host, None, steps=args.steps, warmup=max(1, args.warmup))
+    line = {
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
+        "warmup": max(1, args.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "impl": "reference", "config": {"workload": workload_name(args, fan_out)},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "batches_per_sec": cb["batches_per_sec"], "extract_gbps": cb["extract_gbps"],
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_b200(args, fan_out):
+    import torch.distributed as dist
+    import dgs
+    import dgs_synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        from DistGNN.dist import create_communicator
+        create_communicator(world)
+
+    N, E, D, dt = dgs_synth.SHAPES[args.shape]
+    K, W = args.steps, args.warmup
+    ip, ix, pr, ft = host_graph_from(args, dev)
+    row_bytes = D * ft.element_size()
+    labels = (torch.arange(N, device=dev) % 47).to(torch.int64)
+    host_graph = None
+    if rank == 0 and not args.no_cpu_baseline:
+        host_graph = (ip.cpu().numpy(), ix.cpu().numpy(), pr.cpu().numpy() if pr is not None else None,
+                      ft.cpu().numpy())
+
+    if world == 1:
+        sampler = dgs.classes.CSRSampler(ip, ix, pr)
+
+        def extract(nids):
+            return dgs.ops._CAPI_cuda_index_select(ft, nids, args.extract_algo)
+        layout = "graph + features resident in HBM, un-cached path"
+    else:
+        # shard: node n -> GPU n mod world.  The class API wants the whole graph as pinned CPU tensors
+        # (src/sampling/sampler.cc:64-86); the products shape is small enough for that.
+        cache = torch.arange(rank, N, world, dtype=torch.int64)
+        ipc, ixc, ftc = ip.cpu().pin_memory(), ix.cpu().pin_memory(), ft.cpu().pin_memory()
+        prc = pr.cpu().pin_memory() if pr is not None else torch.Tensor()
+        del ip, ix, ft
+        torch.cuda.empty_cache()
+        sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, cache, rank)
+        fserver = dgs.classes.P2PCacheFeatureServer(ftc, cache, rank)
+
+        def extract(nids):
+            return fserver._CAPI_get_feature(nids, args.extract_algo)
+        layout = f"CSR + features sharded nid mod {world} over {world} GPUs, NVLink peer loads in-kernel"
+
+    # distinct seed batches per rank and per step
+    seeds_all = dgs_synth.seed_batches(N, args.batch, 2 * (K + W) + 2, seed=rank)
+    seeds_dev = seeds_all.to(dev)
+    seeds_pin = seeds_all.pin_memory()
+
+    def step_device(i):
+        blocks = sampler._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+        frontier = blocks[-1][1]
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        x = extract(frontier)
+        ev1.record()
+        return blocks, x, (ev0, ev1)
+
+    lab_host = torch.empty(args.batch, dtype=torch.int64).pin_memory()
+
+    def step_e2e(i):
+        s = seeds_pin[i].to(dev, non_blocking=True)                      # H2D of the step's input
+        blocks = sampler._CAPI_sample_node_classifiction(s, fan_out, False)
+        x = extract(blocks[-1][1])
+        lab = dgs.ops._CAPI_cuda_index_select(labels, s)                  # node_classification.py:228
+        lab_host.copy_(lab, non_blocking=True)                           # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        return blocks, x
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing ("value")
+    for i in range(W):
+        step_device(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = dgs.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    edges = rows = 0
+    ex_events = []
+    e0.record()
+    for i in range(W, W + K):
+        blocks, x, evs = step_device(i)
+        edges += sum(b[2].numel() for b in blocks)
+        rows += x.shape[0]
+        ex_events.append((evs, x.shape[0]))
+    e1.record()
+    barrier()
+    launches = dgs.launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    total_edges = sum_over_ranks(edges)
+    total_rows = sum_over_ranks(rows)
+    ex_ms = sum(a.elapsed_time(b) for (a, b), _ in ex_events)
+    ex_bytes = sum(r * (2 * row_bytes + 8) for _, r in ex_events)
+
+    # ---- end-to-end timing through the plugin API with host seeds / host result ("e2e")
+    for i in range(W):
+        step_e2e(K + W + i)
+    barrier()
+    t_edges = 0
+    e0.record()
+    for i in range(K + 2 * W, 2 * K + 2 * W):
+        blocks, x = step_e2e(i)
+        t_edges += sum(b[2].numel() for b in blocks)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_edges = sum_over_ranks(t_edges)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    achieved = ex_bytes / (ex_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": total_edges / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": workload_name(args, fan_out), "layout": layout,
+                   "l2": "inputs larger than L2 (feature table %.2f GB, CSR %.2f GB, fresh seeds "
+                         "every step)" % (N * row_bytes / 1e9, (E * 8 + N * 8) / 1e9),
+                   "extract_algo": args.extract_algo},
+        "batches_per_sec": world * K / (ms * 1e-3),
+        "extract_gbps": total_rows * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
+        "clocks": clk,
+        "e2e": {"value": e2e_edges / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": args.batch * 8, "d2h_bytes_per_step": args.batch * 8 + 48,
+                "ms_per_step": ms_e2e / K,
+                "note": "seeds from pinned host memory, blocks + features stay on the device (the "
+                        "plugin API returns CUDA tensors), labels of the batch + hop sizes read back"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "gather_rows (feature extract)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes": "rows * (2 * row_bytes + 8)",
+                     "avg_launch_ms": ex_ms / K, "rows_per_launch": rows / K},
+    }
+    if host_graph is not None:
+        cb = cpu_baseline(args, fan_out, host_graph, args.cpu_baseline_seconds)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["batches_per_sec"] = cb["batches_per_sec"]
+        line["cpu_baseline"]["extract_gbps"] = cb["extract_gbps"]
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    fan_out = [int(x) for x in args.fan_out.split(",")]
+    if args.impl == "reference":
+        run_reference(args, fan_out)
+    else:
+        run_b200(args, fan_out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1 @@
+from .communicator import create_communicator, partition_seeds, owner_of

@@ -1,0 +1,340 @@
+// extract.cu - feature-row gather ("extract"), the headline HBM-bound kernel.
+//
+// Replaces the reference's block-per-row, 4-byte-scalar copies
+//   _IndexKernel / _IndexOneDimKernel / GetFeaturesCUDA      src/feature/cuda/feature_ops.cu:140-210
+//   _IndexP2PCacheKernel / GetFeaturesP2PCacheCUDA           src/feature/cuda/feature_ops.cu:38-138
+// with two sm_100a designs over raw row bytes:
+//   algo 1  "ldg":  a CTA stages a tile of row ids in shared memory, resolves every row's source
+//           pointer once (local HBM / NVLink peer shard / pinned host), then all threads copy the
+//           tile as a flat stream of 128-bit vectors (4 independent loads in flight per thread,
+//           L1::no_allocate on both sides, output stores fully coalesced across rows).
+//   algo 2  "tma":  one warp per CTA drives a 4-stage ring of shared-memory tiles with the bulk
+//           async-copy engine: lane r issues cp.async.bulk global->shared for row r (completion on
+//           an mbarrier), lane 0 then writes the whole tile back with ONE cp.async.bulk
+//           shared->global (the output tile is contiguous).  No register staging at all.
+// The location-table probe of the cached path is fused into the row-resolve step (the reference
+// runs it as a separate thrust pass that writes and re-reads a pos_list, feature_ops.cu:92-108).
+#include "dgs_common.cuh"
+#include "p2p_server.h"
+
+namespace dgsb {
+
+struct RowSource {
+  // plain: table != nullptr, loc == nullptr.   cached: loc != nullptr, shards = peer table,
+  // table = host fallback (may be nullptr).
+  const char *table;
+  const LocSlot *loc;
+  uint64_t cap_mask;
+  PtrTable shards;
+};
+
+template <typename IdT>
+__device__ __forceinline__ const char *resolve_row(const RowSource &src, IdT nid, int64_t row_bytes) {
+  if (src.loc != nullptr) {
+    long long v = loc_lookup(src.loc, src.cap_mask, (long long)nid);
+    if (v >= 0) {
+      int dev = (int)((v >> kDevShift) & 0xff);
+      long long idx = v & kIdxMask;
+      return (const char *)src.shards.p[dev] + idx * row_bytes;
+    }
+  }
+  return src.table + (int64_t)nid * row_bytes;
+}
+
+// ---------------------------------------------------------------------------------------------
+// algo 1: flat vector gather.  VecT = int4 (16 B), int2 (8 B) or int (4 B) ... or char.
+template <typename VecT>
+__device__ __forceinline__ VecT ld_stream(const VecT *p) {
+  return *p;
+}
+template <>
+__device__ __forceinline__ int4 ld_stream<int4>(const int4 *p) {
+  return ld_nc_v4(p);
+}
+template <typename VecT>
+__device__ __forceinline__ void st_stream(VecT *p, const VecT &v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void st_stream<int4>(int4 *p, const int4 &v) {
+  st_na_v4(p, v);
+}
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherRows = 64;   // rows per tile
+constexpr int kGatherUnroll = 4;
+
+template <typename IdT, typename VecT>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_rows_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64_t row_bytes,
+                   uint32_t vpr /* vectors per row */, uint32_t vpr_magic, char *__restrict__ out) {
+  __shared__ const char *s_src[kGatherRows];
+  const int64_t num_tiles = (n + kGatherRows - 1) / kGatherRows;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kGatherRows;
+    const int rows = (int)min((int64_t)kGatherRows, n - row0);
+    __syncthreads();  // previous tile's readers are done with s_src
+    if (threadIdx.x < rows) {
+      IdT nid = nids[row0 + threadIdx.x];
+      s_src[threadIdx.x] = resolve_row<IdT>(src, nid, row_bytes);
+    }
+    __syncthreads();
+    const uint32_t total = (uint32_t)rows * vpr;
+    VecT *otile = reinterpret_cast<VecT *>(out + row0 * row_bytes);
+    for (uint32_t base = threadIdx.x; base < total; base += kGatherThreads * kGatherUnroll) {
+      VecT v[kGatherUnroll];
+#pragma unroll
+      for (int u = 0; u < kGatherUnroll; ++u) {
+        uint32_t e = base + u * kGatherThreads;
+        if (e < total) {
+          uint32_t r = __umulhi(e, vpr_magic);  // e / vpr, exact for e < 2^16 (host-checked)
+          uint32_t c = e - r * vpr;
+          v[u] = ld_stream<VecT>(reinterpret_cast<const VecT *>(s_src[r]) + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGatherUnroll; ++u) {
+        uint32_t e = base + u * kGatherThreads;
+        if (e < total) st_stream<VecT>(otile + e, v[u]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// algo 2: TMA bulk-copy ring (row_bytes % 16 == 0, 16-byte aligned tables).
+constexpr int kTmaRows = 32;      // rows per stage = one per lane
+constexpr int kTmaPrefetch = 3;   // tiles of row loads in flight per warp
+constexpr int kTmaPendingSt = 2;  // bulk stores allowed to be still reading shared memory
+constexpr int kTmaStages = kTmaPrefetch + kTmaPendingSt + 1;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(32)
+gather_rows_tma_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64_t row_bytes,
+                       char *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [stages][kTmaRows * row_bytes] then mbarriers
+  const uint32_t stage_bytes = (uint32_t)(kTmaRows * row_bytes);
+  unsigned char *bufs = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kTmaStages * stage_bytes);
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int64_t num_tiles = (n + kTmaRows - 1) / kTmaRows;
+  // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  int64_t issue_tile = blockIdx.x;   // next tile to issue loads for
+  int64_t drain_tile = blockIdx.x;   // next tile to store
+  uint32_t issue_it = 0, drain_it = 0;
+
+  auto issue = [&](int64_t tile, uint32_t it) {
+    const int s = it % kTmaStages;
+    const int64_t row0 = tile * kTmaRows;
+    const int rows = (int)min((int64_t)kTmaRows, n - row0);
+    if (it >= (uint32_t)kTmaStages) {
+      // the bulk store that last read this stage must have finished reading shared memory.
+      // stores are committed one group per tile, in order.  When tile `it` is issued, tiles
+      // 0 .. it-prefetch-1 have been committed; allowing the newest kTmaPendingSt of them to be
+      // pending guarantees the group of tile (it - stages) has finished reading its stage.
+      if (lane == 0) bulk_wait_read<kTmaPendingSt>();
+      __syncwarp();
+    }
+    const uint32_t bar = smem_u32(&bars[s]);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(rows * row_bytes));
+    __syncwarp();
+    if (lane < rows) {
+      IdT nid = nids[row0 + lane];
+      const char *p = resolve_row<IdT>(src, nid, row_bytes);
+      bulk_g2s(smem_u32(bufs + (size_t)s * stage_bytes + (size_t)lane * row_bytes), p,
+               (uint32_t)row_bytes, bar);
+    }
+  };
+  auto drain = [&](int64_t tile, uint32_t it) {
+    const int s = it % kTmaStages;
+    const uint32_t parity = (it / kTmaStages) & 1u;
+    const int64_t row0 = tile * kTmaRows;
+    const int rows = (int)min((int64_t)kTmaRows, n - row0);
+    mbar_wait(smem_u32(&bars[s]), parity);
+    if (lane == 0) {
+      bulk_s2g(out + row0 * row_bytes, smem_u32(bufs + (size_t)s * stage_bytes),
+               (uint32_t)(rows * row_bytes));
+      bulk_commit();
+    }
+    __syncwarp();
+  };
+
+  // prologue: kTmaPrefetch tiles of loads in flight
+  for (int p = 0; p < kTmaPrefetch && issue_tile < num_tiles; ++p) {
+    issue(issue_tile, issue_it);
+    issue_tile += gridDim.x;
+    ++issue_it;
+  }
+  while (drain_tile < num_tiles) {
+    if (issue_tile < num_tiles) {
+      issue(issue_tile, issue_it);
+      issue_tile += gridDim.x;
+      ++issue_it;
+    }
+    drain(drain_tile, drain_it);
+    drain_tile += gridDim.x;
+    ++drain_it;
+  }
+  if (lane == 0) bulk_wait_all();
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t div_magic(uint32_t d) { return (uint32_t)(((1ull << 32) + d - 1) / d); }
+
+template <typename IdT>
+static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64_t row_bytes,
+                         char *out, int algo, bool all_aligned16, cudaStream_t st) {
+  if (n == 0) return 0;
+  const bool can_tma = all_aligned16 && (row_bytes % 16 == 0) && row_bytes >= 16 &&
+                       (size_t)kTmaStages * kTmaRows * row_bytes + 64 <= 200 * 1024;
+  if (algo == 2 && !can_tma) {
+    set_error("extract: TMA path needs 16-byte aligned tables and row_bytes %% 16 == 0 "
+              "(row_bytes=%lld)", (long long)row_bytes);
+    return 1;
+  }
+  if (algo == 0) algo = 1;  // default: vectorised gather (see DESIGN.md for the measured choice)
+  if (algo == 2) {
+    size_t smem = (size_t)kTmaStages * kTmaRows * row_bytes + kTmaStages * sizeof(uint64_t);
+    auto kern = gather_rows_tma_kernel<IdT>;
+    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    int grid = grid_for(n, kTmaRows, per_sm);
+    kern<<<grid, 32, smem, st>>>(src, nids, n, row_bytes, out);
+    DGS_LAUNCH_CHECK();
+    return 0;
+  }
+  int grid = grid_for(n, kGatherRows, 8);
+  if (all_aligned16 && row_bytes % 16 == 0) {
+    uint32_t vpr = (uint32_t)(row_bytes / 16);
+    DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large for the "
+                "tile index math (max %d)", (long long)row_bytes, 65535 / kGatherRows * 16);
+    gather_rows_kernel<IdT, int4><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
+                                                                   div_magic(vpr), out);
+  } else if (row_bytes % 8 == 0) {
+    uint32_t vpr = (uint32_t)(row_bytes / 8);
+    DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
+                (long long)row_bytes);
+    gather_rows_kernel<IdT, int2><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
+                                                                   div_magic(vpr), out);
+  } else if (row_bytes % 4 == 0) {
+    uint32_t vpr = (uint32_t)(row_bytes / 4);
+    DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
+                (long long)row_bytes);
+    gather_rows_kernel<IdT, int><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
+                                                                  div_magic(vpr), out);
+  } else {
+    uint32_t vpr = (uint32_t)row_bytes;
+    DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
+                (long long)row_bytes);
+    gather_rows_kernel<IdT, char><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
+                                                                   div_magic(vpr), out);
+  }
+  DGS_LAUNCH_CHECK();
+  return 0;
+}
+
+static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+}  // namespace dgsb
+
+using namespace dgsb;
+
+extern "C" int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids,
+                                int64_t n, void *out, int algo, void *stream) {
+  DGS_REQUIRE(n >= 0 && row_bytes > 0, "dgs_index_select: bad sizes n=%lld row_bytes=%lld",
+              (long long)n, (long long)row_bytes);
+  if (n == 0) return 0;
+  DGS_REQUIRE(table && nids && out, "dgs_index_select: null pointer");
+  RowSource src;
+  memset(&src, 0, sizeof(src));
+  src.table = (const char *)table;
+  bool al = aligned16(table) && aligned16(out);
+  DGS_ITYPE_SWITCH(itype, IdT, {
+    return launch_gather<IdT>(src, (const IdT *)nids, n, row_bytes, (char *)out, algo, al,
+                              (cudaStream_t)stream);
+  });
+  return 0;
+}
+
+extern "C" int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_table,
+                               int64_t row_bytes, const void *loc_table, int64_t capacity,
+                               int itype, const void *nids, int64_t n, void *out, int algo,
+                               void *stream) {
+  DGS_REQUIRE(n >= 0 && row_bytes > 0, "dgs_extract_p2p: bad sizes");
+  if (n == 0) return 0;
+  DGS_REQUIRE(feat && loc_table && nids && out, "dgs_extract_p2p: null pointer");
+  DGS_REQUIRE(capacity > 0 && (capacity & (capacity - 1)) == 0,
+              "dgs_extract_p2p: capacity must be a power of two");
+  RowSource src;
+  memset(&src, 0, sizeof(src));
+  src.table = (const char *)host_table;
+  src.loc = (const LocSlot *)loc_table;
+  src.cap_mask = (uint64_t)capacity - 1;
+  bool al = aligned16(out) && (host_table == nullptr || aligned16(host_table));
+  for (int d = 0; d < feat->world; ++d) {
+    src.shards.p[d] = feat->ptrs[d];
+    al = al && aligned16(feat->ptrs[d]);
+  }
+  DGS_ITYPE_SWITCH(itype, IdT, {
+    return launch_gather<IdT>(src, (const IdT *)nids, n, row_bytes, (char *)out, algo, al,
+                              (cudaStream_t)stream);
+  });
+  return 0;
+}

@@ -1,0 +1,14 @@
+// p2p_server.h - internal layout of dgs_p2p_server (C-ABI handle in include/dgs_b200.h).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/dgs_b200.h"
+
+struct dgs_p2p_server {
+  int world;
+  int rank;
+  int owns_local;      // local shard was cudaMalloc'ed by us
+  int ipc_opened;      // peers were opened with cudaIpcOpenMemHandle
+  void *ptrs[DGS_MAX_DEVICES];
+  int64_t nbytes[DGS_MAX_DEVICES];
+};

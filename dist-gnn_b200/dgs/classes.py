@@ -1,0 +1,444 @@
+"""``dgs.classes`` - TensorP2PServer, P2PCacheSampler, P2PCacheFeatureServer with the reference's
+constructor / method names (src/pybind.cc:17-45), implemented over the sm_100a C-ABI library."""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._util import (check_cpu, check_cuda, contiguous, itype, ptr, stream, tensor_from_ptr, zero_ws)
+
+lib = _lib.lib
+check = _lib.check
+
+
+def _barrier():
+    check(lib().dgs_nccl_barrier(), "barrier")
+
+
+class TensorP2PServer:
+    """cache::TensorP2PServer (src/cache/tensor_p2p_cache.h:43-73, tensor_p2p_cache.cc:11-132).
+
+    Copies a CUDA tensor into a raw cudaMalloc shard and maps every peer's shard through CUDA IPC.
+    Construction is collective over the NCCL context.  Unlike the reference the destructor does NOT
+    run a collective (tensor_p2p_cache.cc:115 barriers inside ~TensorP2PServer, which deadlocks under
+    Python GC ordering); call ``close()`` on all ranks for a synchronised teardown."""
+
+    def __init__(self, tensor, _uninitialised_shape=None, _dtype=None, _device=None):
+        self._handle = None
+        if _uninitialised_shape is not None:
+            shape, dtype, device = tuple(_uninitialised_shape), _dtype, _device
+            src = None
+        else:
+            check_cuda(tensor, "tensor")
+            if tensor.dim() < 1 or tensor.shape[0] <= 0:
+                raise RuntimeError("TensorP2PServer: first dimension must be > 0")
+            tensor = tensor.contiguous()
+            shape, dtype, device = tuple(tensor.shape), tensor.dtype, tensor.device
+            src = ptr(tensor)
+        self._shape = shape
+        self._dtype = dtype
+        self._device = device
+        self._esize = torch.empty(0, dtype=dtype).element_size()
+        stride = 1
+        for d in shape[1:]:
+            stride *= d
+        self.item_stride_ = stride
+        nbytes = shape[0] * stride * self._esize
+        if nbytes <= 0:
+            raise RuntimeError("TensorP2PServer: empty tensor")
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            torch.cuda.current_stream().synchronize()  # the source was produced on this stream
+            check(lib().dgs_p2p_server_create(src, nbytes, C.byref(h)), "TensorP2PServer")
+        self._handle = h
+        self.world = lib().dgs_p2p_server_world(h)
+        self.rank = lib().dgs_p2p_server_rank(h)
+
+    @classmethod
+    def _empty(cls, shape, dtype, device):
+        """Extension: allocate the shard without a staging copy (the caller fills it in place)."""
+        return cls(None, _uninitialised_shape=shape, _dtype=dtype, _device=device)
+
+    @classmethod
+    def _virtual(cls, tensors, rank):
+        """Extension (tests): adopt tensors of this process as the shards of `len(tensors)`
+        emulated ranks, seen from emulated rank `rank`."""
+        self = cls.__new__(cls)
+        t0 = tensors[rank]
+        self._shape, self._dtype, self._device = tuple(t0.shape), t0.dtype, t0.device
+        self._esize = t0.element_size()
+        stride = 1
+        for d in t0.shape[1:]:
+            stride *= d
+        self.item_stride_ = stride
+        self._keep = [t.contiguous() for t in tensors]
+        ptrs = _lib.vp_array([t.data_ptr() for t in self._keep])
+        nb = _lib.i64_array([t.numel() * t.element_size() for t in self._keep])
+        h = C.c_void_p()
+        check(lib().dgs_p2p_server_create_virtual(len(tensors), rank, ptrs, nb, C.byref(h)),
+              "TensorP2PServer._virtual")
+        self._handle = h
+        self.world = len(tensors)
+        self.rank = rank
+        return self
+
+    # -- reference API
+    def _CAPI_get_local_device_tensor(self):
+        """GetLocalDeviceTensor (tensor_p2p_cache.cc:120-125): local shard, original shape."""
+        l = lib()
+        return tensor_from_ptr(l.dgs_p2p_server_ptr(self._handle, self.rank),
+                               l.dgs_p2p_server_nbytes(self._handle, self.rank), self._dtype,
+                               self._shape, owner=self, device=self._device)
+
+    def _CAPI_get_device_tensor(self, device_id):
+        """GetDeviceTensor (tensor_p2p_cache.cc:127-132): flat 1-D view of device_id's shard."""
+        l = lib()
+        if not 0 <= device_id < self.world:
+            raise RuntimeError(f"device_id {device_id} out of range [0, {self.world})")
+        nb = l.dgs_p2p_server_nbytes(self._handle, device_id)
+        return tensor_from_ptr(l.dgs_p2p_server_ptr(self._handle, device_id), nb, self._dtype,
+                               (nb // self._esize,), owner=self, device=self._device)
+
+    def close(self, barrier=True):
+        if self._handle is not None:
+            h, self._handle = self._handle, None
+            check(lib().dgs_p2p_server_destroy(h, 1 if barrier else 0), "TensorP2PServer.close")
+
+    def __del__(self):
+        try:
+            self.close(barrier=False)
+        except Exception:
+            pass
+
+
+def _build_loc_table(local_nids, num_nodes, device):
+    """All-gather the per-rank cached id lists and build the packed location table
+    (CreateNidsP2PCacheHashMapCUDA, src/hashmap/cuda/hashmap.cu:15-77).  Returns
+    (table int64[2*cap], capacity, n_unique, per-rank id lists)."""
+    l = lib()
+    world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
+    lists = ops._allgather_tensors(local_nids)
+    if world > 1:
+        # |union| exactly like the reference: bool mask + count (sampler.cc:117-125)
+        mask = torch.zeros(num_nodes, dtype=torch.bool, device=device)
+        for t in lists:
+            mask[t.long()] = True
+        n_unique = int(mask.sum().item())
+        del mask
+    else:
+        n_unique = local_nids.numel()
+    cap = l.dgs_loc_table_capacity(n_unique)
+    table = torch.empty(cap * 2, dtype=torch.int64, device=device)
+    check(l.dgs_loc_table_build(ptr(table), cap, itype(local_nids, "cache_nids"), world, rank,
+                                _lib.vp_array([ptr(t) for t in lists]),
+                                _lib.i64_array([t.numel() for t in lists]), stream()),
+          "location table build")
+    return table, cap, n_unique, lists
+
+
+def _unpack_loc_table(table, cap, dtype):
+    key = torch.empty(cap, dtype=dtype, device=table.device)
+    idx = torch.empty_like(key)
+    dev = torch.empty_like(key)
+    check(lib().dgs_loc_table_unpack(ptr(table), cap, itype(key), ptr(key), ptr(idx), ptr(dev),
+                                     stream()), "location table unpack")
+    return key, idx, dev
+
+
+def _host_source(t, name, all_cached):
+    """Pointer the kernels use for cache misses (the caller's pinned CPU tensor)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.is_pinned():
+        return t.data_ptr()
+    if all_cached:
+        return None  # never dereferenced
+    raise RuntimeError(f"{name} must be pinned (torch pin_memory or _CAPI_tensor_pin_memory): "
+                       "un-cached nodes are read from it by the GPU")
+
+
+class _BlockPipeline:
+    """Multi-hop sample + relabel over one dgs_graph_t with persistent workspaces: every hop is
+    enqueued with device-side counts (dgs_sample_blocks) and the host reads the 2 L counts once."""
+
+    def __init__(self, graph, device, id_dtype):
+        self._graph = graph
+        self._device = device
+        self._id_dtype = id_dtype
+        self._ws = None          # sampling workspace
+        self._rl_table = None    # persistent relabel table (kept all-0xFF between calls)
+        self._rl_ws = None
+        self._rl_cap = 0
+        self._rl_items = 0
+        self._max_seeds = 0
+        self._counts_host = None
+
+    def _reserve(self, max_seeds, max_items):
+        l = lib()
+        if self._ws is None or max_seeds > self._max_seeds:
+            self._ws = zero_ws(l.dgs_sample_ws_bytes(max_seeds), self._device)
+            self._max_seeds = max_seeds
+        cap = l.dgs_relabel_table_capacity(max_items)
+        if self._rl_table is None or cap > self._rl_cap:
+            self._rl_table = torch.full((cap * 2,), -1, dtype=torch.int64, device=self._device)
+            self._rl_cap = cap
+        if self._rl_ws is None or max_items > self._rl_items:
+            self._rl_ws = zero_ws(l.dgs_relabel_ws_bytes(max_items), self._device)
+            self._rl_items = max_items
+
+    def sample(self, seeds, fan_out, replace=False, rng_seed=None):
+        l = lib()
+        check_cuda(seeds, "seeds")
+        if seeds.dtype != self._id_dtype:
+            raise RuntimeError("seeds must have the id type of indices")
+        fan_out = [int(k) for k in fan_out]
+        L = len(fan_out)
+        if L == 0:
+            return []
+        seeds = seeds.contiguous()
+        if rng_seed is None:
+            rng_seed = l.dgs_randn_uint64()
+        if any(k < 0 for k in fan_out) or seeds.numel() == 0:
+            return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
+        with torch.cuda.device(self._device):
+            S = seeds.numel()
+            ubs, nnz_ubs = [], []
+            ub = S
+            for li in range(L):
+                k = fan_out[L - 1 - li]
+                ubs.append(ub)
+                nnz_ubs.append(ub * k)
+                ub = ub + ub * k
+            self._reserve(max(ubs), ub)
+            total = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
+            arena = torch.empty(total, dtype=seeds.dtype, device=self._device)
+            fr, rows, cols = [], [], []
+            off = 0
+            for u, n in zip(ubs, nnz_ubs):
+                fr.append(arena[off:off + u + n]); off += u + n
+                rows.append(arena[off:off + n]); off += n
+                cols.append(arena[off:off + n]); off += n
+            counts_dev = torch.empty(2 * L, dtype=torch.int64, device=self._device)
+            check(l.dgs_sample_blocks(
+                C.byref(self._graph), ptr(seeds), S, L, _lib.i64_array(fan_out),
+                int(bool(replace)), C.c_uint64(rng_seed),
+                _lib.vp_array([t.data_ptr() for t in fr]),
+                _lib.vp_array([t.data_ptr() if t.numel() else None for t in rows]),
+                _lib.vp_array([t.data_ptr() if t.numel() else None for t in cols]),
+                _lib.i64_array(nnz_ubs), _lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
+                ptr(counts_dev), ptr(self._ws), ptr(self._rl_table), self._rl_cap,
+                ptr(self._rl_ws), stream()), "sample_blocks")
+            if self._counts_host is None or self._counts_host.numel() < 2 * L:
+                self._counts_host = torch.empty(2 * L, dtype=torch.int64).pin_memory()
+            ch = self._counts_host[:2 * L]
+            ch.copy_(counts_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the only host sync of the batch
+            counts = ch.tolist()
+        out = []
+        cur = seeds
+        for li in range(L):
+            nnz, nf = counts[2 * li], counts[2 * li + 1]
+            frontier = fr[li][:nf]
+            out.append((cur, frontier, rows[li][:nnz], cols[li][:nnz]))
+            cur = frontier
+        return out
+
+    def _sample_per_hop(self, seeds, fan_out, replace, rng_seed):
+        """Host-synchronised hop loop (used for fan-out -1 = all neighbours, an extension)."""
+        out = []
+        cur = seeds
+        with torch.cuda.device(self._device):
+            for li, k in enumerate(reversed(fan_out)):
+                key = (rng_seed + 0x9E3779B97F4A7C15 * (li + 1)) & 0xFFFFFFFFFFFFFFFF
+                row, col = ops._sample_one_hop(self._graph, cur, k, replace, key)
+                frontier, (rrow, rcol) = ops._relabel([cur, col], [row, col])
+                out.append((cur, frontier, rrow, rcol))
+                cur = frontier
+        return out
+
+
+class CSRSampler:
+    """Extension (no reference counterpart): the fused multi-hop pipeline over an UN-cached CSR that
+    lives in device memory or pinned host memory - the "no cache" configuration, which in the
+    reference is a Python loop over ops._CAPI_cuda_sample_neighbors + _CAPI_cuda_sampled_tensor_
+    relabel with two host syncs per hop.  Same result tuples as P2PCacheSampler."""
+
+    def __init__(self, indptr, indices, probs=None, device=None):
+        ops._check_sampling_args(torch.empty(0, dtype=indices.dtype, device="cuda"), indptr, indices,
+                                 probs if probs is not None and probs.numel() else None)
+        self._keep = (indptr, indices, probs)
+        if device is None:
+            device = indices.device if indices.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        g = ops._make_graph(indptr, indices, probs if probs is not None and probs.numel() else None)
+        self._pipe = _BlockPipeline(g, device, indices.dtype)
+
+    def _CAPI_sample_node_classifiction(self, seeds, fan_out, replace=False, rng_seed=None):
+        return self._pipe.sample(seeds, fan_out, replace, rng_seed)
+
+
+class P2PCacheSampler:
+    """sampling::P2PCacheSampler (src/sampling/sampler.h:39-73, sampler.cc:64-196)."""
+
+    def __init__(self, indptr, indices, probs, cache_nids, device_id):
+        l = lib()
+        check_cpu(indptr, "indptr")
+        check_cpu(indices, "indices")
+        check_cpu(probs, "probs")
+        if device_id != l.dgs_nccl_rank():
+            raise RuntimeError(f"device_id ({device_id}) must equal the NCCL rank "
+                               f"({l.dgs_nccl_rank()})")
+        if cache_nids.numel() == 0:
+            raise RuntimeError("cache_nids must not be empty (use dgs.ops._CAPI_cuda_sample_"
+                               "neighbors for the un-cached path)")
+        contiguous(indptr, "indptr")
+        contiguous(indices, "indices")
+        self.device_id_ = int(device_id)
+        self._device = torch.device("cuda", self.device_id_)
+        self.bias_ = probs.numel() > 0
+        if self.bias_ and probs.dtype != torch.float32:
+            raise RuntimeError("probs must be float32")
+        self.cpu_indptr_, self.cpu_indices_ = indptr, indices
+        self.cpu_probs_ = probs if self.bias_ else None
+        num_nodes = indptr.numel() - 1
+        for t in (indptr, indices) + ((probs,) if self.bias_ else ()):
+            if not t.is_pinned():
+                raise RuntimeError("indptr / indices / probs must be pinned CPU tensors: the "
+                                   "sub-CSR of the cached nodes is extracted by the GPU from them")
+        with torch.cuda.device(self._device):
+            nids = cache_nids.to(self._device).contiguous()
+            if nids.dtype != indices.dtype:
+                nids = nids.to(indices.dtype)
+            sub_indptr = ops._Test_ExtractIndptr(nids, indptr)
+            self.gpu_indptr_ = TensorP2PServer(sub_indptr)
+            sub_indices = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, indices)
+            # a cached set without edges still needs a non-empty shard for IPC
+            self.gpu_indices_ = TensorP2PServer(
+                sub_indices if sub_indices.numel() else torch.zeros(1, dtype=indices.dtype,
+                                                                    device=self._device))
+            self._num_cached_edges = sub_indices.numel()
+            self.gpu_probs_ = None
+            if self.bias_:
+                sub_probs = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, probs)
+                self.gpu_probs_ = TensorP2PServer(
+                    sub_probs if sub_probs.numel() else torch.zeros(1, dtype=probs.dtype,
+                                                                    device=self._device))
+            self._table, self._cap, self._n_unique, _ = _build_loc_table(nids, num_nodes,
+                                                                         self._device)
+            torch.cuda.current_stream().synchronize()
+            _barrier()
+        all_cached = self._n_unique >= num_nodes
+        g = _lib.Graph()
+        g.itype = itype(indices, "indices")
+        g.etype = itype(indptr, "indptr")
+        g.indptr = _host_source(indptr, "indptr", all_cached)
+        g.indices = _host_source(indices, "indices", all_cached)
+        g.probs = _host_source(probs, "probs", all_cached) if self.bias_ else None
+        g.p2p_indptr = self.gpu_indptr_._handle
+        g.p2p_indices = self.gpu_indices_._handle
+        g.p2p_probs = self.gpu_probs_._handle if self.bias_ else None
+        g.loc_table = ptr(self._table)
+        g.loc_capacity = self._cap
+        self._graph = g
+        self._pipe = _BlockPipeline(g, self._device, indices.dtype)
+
+    def _CAPI_sample_node_classifiction(self, seeds, fan_out, replace=False, rng_seed=None):
+        """NodeClassifictionSample (sampler.cc:146-166): list over hops, seed-side hop first, of
+        (seeds, frontier, coo_row, coo_col) with coo_* relabelled to positions in frontier."""
+        return self._pipe.sample(seeds, fan_out, replace, rng_seed)
+
+    def _CAPI_get_cpu_structure_tensors(self):
+        """GetCPUStructureTensors (sampler.cc:168-178); probs is None for a uniform sampler (the
+        reference returns an undefined tensor)."""
+        return self.cpu_indptr_, self.cpu_indices_, self.cpu_probs_
+
+    def _CAPI_get_local_cache_structure_tensors(self):
+        """GetLocalCachedStructureTensors (sampler.cc:180-191)."""
+        idx = self.gpu_indices_._CAPI_get_local_device_tensor()[:self._num_cached_edges]
+        pr = None
+        if self.bias_:
+            pr = self.gpu_probs_._CAPI_get_local_device_tensor()[:self._num_cached_edges]
+        return self.gpu_indptr_._CAPI_get_local_device_tensor(), idx, pr
+
+    def _CAPI_get_local_cache_hashmap_tensors(self):
+        """GetLocalCachedHashTensors (sampler.cc:193-196): (key, idx, devid).  Synthesised from the
+        packed table; the slot layout is implementation-defined (it is race-dependent in the
+        reference as well), only lookups are comparable."""
+        with torch.cuda.device(self._device):
+            return _unpack_loc_table(self._table, self._cap, self.cpu_indices_.dtype)
+
+    def close(self, barrier=True):
+        for s in (self.gpu_indptr_, self.gpu_indices_, self.gpu_probs_):
+            if s is not None:
+                s.close(barrier)
+
+
+class P2PCacheFeatureServer:
+    """feature::P2PCacheFeatureServer (src/feature/feature_sever.h:10-34, feature_server.cc:10-86)."""
+
+    def __init__(self, data, cache_nids, device_id):
+        l = lib()
+        check_cpu(data, "data")
+        if device_id != l.dgs_nccl_rank():
+            raise RuntimeError(f"device_id ({device_id}) must equal the NCCL rank "
+                               f"({l.dgs_nccl_rank()})")
+        if cache_nids.numel() == 0:
+            raise RuntimeError("cache_nids must not be empty (use dgs.ops._CAPI_cuda_index_select "
+                               "for the un-cached path)")
+        contiguous(data, "data")
+        self.device_id_ = int(device_id)
+        self._device = torch.device("cuda", self.device_id_)
+        self.cpu_features_ = data
+        num_items = data.shape[0]
+        stride = 1
+        for d in data.shape[1:]:
+            stride *= d
+        self._stride = stride
+        self._row_bytes = stride * data.element_size()
+        with torch.cuda.device(self._device):
+            nids = cache_nids.to(self._device).contiguous()
+            shape = (nids.numel(),) + tuple(data.shape[1:])
+            if data.is_pinned():
+                # gather the cached rows straight from pinned host memory into the shard
+                # (the reference index_selects on the CPU, then copies, feature_server.cc:33-35)
+                self.gpu_features_ = TensorP2PServer._empty(shape, data.dtype, self._device)
+                local = self.gpu_features_._CAPI_get_local_device_tensor()
+                check(l.dgs_index_select(ptr(data), self._row_bytes, itype(nids, "cache_nids"),
+                                         ptr(nids), nids.numel(), ptr(local), 1, stream()),
+                      "feature shard build")
+                torch.cuda.current_stream().synchronize()
+            else:
+                sub = data.index_select(0, cache_nids.cpu().long()).to(self._device)
+                self.gpu_features_ = TensorP2PServer(sub)
+            self._table, self._cap, self._n_unique, _ = _build_loc_table(nids, num_items,
+                                                                         self._device)
+            torch.cuda.current_stream().synchronize()
+            _barrier()
+        self._host_ptr = _host_source(data, "data", self._n_unique >= num_items)
+        self._itype_dtype = nids.dtype
+
+    def _CAPI_get_cpu_feature(self):
+        return self.cpu_features_
+
+    def _CAPI_get_gpu_feature(self):
+        return self.gpu_features_._CAPI_get_local_device_tensor()
+
+    def _CAPI_get_feature(self, nids, algo=0):
+        """GetFeatures (feature_server.cc:69-74) -> [len(nids), prod(data.shape[1:])]."""
+        check_cuda(nids, "nids")
+        nids = nids.contiguous()
+        n = nids.numel()
+        out = torch.empty((n, self._stride), dtype=self.cpu_features_.dtype, device=nids.device)
+        if n:
+            check(lib().dgs_extract_p2p(self.gpu_features_._handle, self._host_ptr,
+                                        self._row_bytes, ptr(self._table), self._cap,
+                                        itype(nids, "nids"), ptr(nids), n, ptr(out), int(algo),
+                                        stream()), "_CAPI_get_feature")
+        return out
+
+    def _CAPI_get_local_cache_hashmap_tensors(self):
+        """Extension (tests): the (key, idx, devid) view of the location table."""
+        with torch.cuda.device(self._device):
+            return _unpack_loc_table(self._table, self._cap, self._itype_dtype)
+
+    def close(self, barrier=True):
+        self.gpu_features_.close(barrier)

@@ -1,0 +1,212 @@
+/*
+ * dgs_b200.h - C-ABI of the B200-native (sm_100a) mini-batch data path that replaces
+ * CommediaJW/Dist-GNN's `dgs` plugin kernels.
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers + sizes, no torch / pybind types.
+ *   - every entry returns 0 on success, non-zero on error; dgs_last_error() gives the text
+ *     (argument errors are recoverable; the reference exit()s / abort()s on CUDA / NCCL errors,
+ *     src/common/dgs_headers.h:11-34 - we report instead).
+ *   - the library never allocates per-call memory: all inputs, outputs and workspaces are
+ *     caller-owned device buffers (the Python host allocates them with torch), everything is
+ *     enqueued on the caller's stream and nothing synchronises unless the entry says so.
+ *   - ids are int32 or int64 (DGS_ID_TYPE_SWITCH, src/common/dgs_headers.h:47-58), indptr has
+ *     its own int32/int64 type, edge weights are float32.
+ *
+ * Each block below cites the reference interface (file:line under the reference tree) it
+ * replaces.  The Python binding that a reference maintainer would add is in INTEGRATION.md.
+ */
+#ifndef DGS_B200_H_
+#define DGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGS_B200_ABI_VERSION 1
+#define DGS_MAX_DEVICES 16
+
+typedef enum { DGS_I32 = 0, DGS_I64 = 1 } dgs_itype_t;
+
+/* ------------------------------------------------------------------ misc / errors */
+int dgs_abi_version(void);
+const char *dgs_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t dgs_launch_count(void);
+/* SM count of the current device (grid sizing), cached. */
+int dgs_sm_count(void);
+
+/* ------------------------------------------------------------------ random engine
+ * replaces RandomEngine / ctx::randn_uint64  (src/context/context.h:7-20, context.cc:6).
+ * dgs_seed() is an extension: the reference seeds from std::random_device and is not
+ * reproducible. */
+uint64_t dgs_randn_uint64(void);
+void dgs_seed(uint64_t seed);
+
+/* ------------------------------------------------------------------ pin memory
+ * replaces TensorPinMemory / TensorUnpinMemory  (src/common/pin_memory.cc:7-19). */
+int dgs_host_register(void *host_ptr, size_t nbytes);
+int dgs_host_unregister(void *host_ptr);
+
+/* ------------------------------------------------------------------ NCCL context
+ * replaces nccl::GetUniqueId / SetNCCL / NCCLContext::{Barrier_, NCCLTensorAllGather_}
+ * (src/nccl/nccl_context.cc:13-112).  One process-global communicator, as in the reference. */
+int dgs_nccl_get_unique_id(int64_t out_id[16]);
+int dgs_nccl_set(int nranks, const int64_t id[16], int rank);
+int dgs_nccl_rank(void);   /* 0 before dgs_nccl_set */
+int dgs_nccl_world(void);  /* 1 before dgs_nccl_set */
+int dgs_nccl_barrier(void);
+/* all-gather of one int64 per rank -> host array out[world]. */
+int dgs_nccl_allgather_i64(int64_t value, int64_t *out_host);
+/* variable-size all-gather of raw bytes: rank r's send buffer lands in recv_dev[r] on every
+ * rank (recv_dev[rank] may equal send_dev: skipped).  Blocking. */
+int dgs_nccl_allgatherv(const void *send_dev, int64_t send_bytes, void *const *recv_dev,
+                        const int64_t *recv_bytes);
+
+/* ------------------------------------------------------------------ tensor p2p server
+ * replaces cache::TensorP2PServer + tensor_p2p_server_wrapper::At
+ * (src/cache/tensor_p2p_cache.h:11-73, tensor_p2p_cache.cc:11-132).
+ * A shard is one raw cudaMalloc copy of the caller's device buffer; every rank of the NCCL
+ * context gets a void*[world] table of CUDA-IPC mapped peer shards. */
+typedef struct dgs_p2p_server dgs_p2p_server_t;
+/* collective over the NCCL context (world 1: purely local).  dev_src == NULL allocates the shard
+ * without copying (the caller fills dgs_p2p_server_ptr(s, rank) in place). */
+int dgs_p2p_server_create(const void *dev_src, int64_t nbytes, dgs_p2p_server_t **out);
+/* non-collective: adopt `world` pointers that already live in this process (emulated ranks on
+ * one GPU for tests; shards are NOT owned / freed). */
+int dgs_p2p_server_create_virtual(int world, int rank, void *const *ptrs, const int64_t *nbytes,
+                                  dgs_p2p_server_t **out);
+void *dgs_p2p_server_ptr(const dgs_p2p_server_t *s, int dev);
+int64_t dgs_p2p_server_nbytes(const dgs_p2p_server_t *s, int dev);
+int dgs_p2p_server_world(const dgs_p2p_server_t *s);
+int dgs_p2p_server_rank(const dgs_p2p_server_t *s);
+/* collective when barrier != 0 (the reference barriers in its destructor,
+ * tensor_p2p_cache.cc:105-118). */
+int dgs_p2p_server_destroy(dgs_p2p_server_t *s, int barrier);
+
+/* ------------------------------------------------------------------ location table
+ * replaces hashmap::cuda::Hashmap + CreateNidsP2PCacheHashMapCUDA
+ * (src/hashmap/cuda/hashmap.h:12-95, hashmap.cu:15-77).
+ * Layout: capacity x 16-byte slots {int64 key; int64 val}, key -1 = empty,
+ * val = prio<<56 | dev<<48 | idx.  One 128-bit load per probe, linear probing. */
+int64_t dgs_loc_table_capacity(int64_t n_unique); /* 2 * 2^(floor(log2 n)+1), hashmap.cu:20 */
+int dgs_loc_table_build(void *table, int64_t capacity, int itype, int world, int rank,
+                        const void *const *dev_nids, const int64_t *counts, void *stream);
+/* per query: out_dev[i], out_idx[i] (same itype as ids), -1/-1 on miss. */
+int dgs_loc_table_lookup(const void *table, int64_t capacity, int itype, const void *nids,
+                         int64_t n, void *out_dev, void *out_idx, void *stream);
+/* the three reference-visible tensors (key, idx, devid), hashmap.cu:21-35. */
+int dgs_loc_table_unpack(const void *table, int64_t capacity, int itype, void *key, void *idx,
+                         void *devid, void *stream);
+
+/* ------------------------------------------------------------------ feature extract
+ * replaces GetFeaturesCUDA / _IndexKernel (src/feature/cuda/feature_ops.cu:140-210) and
+ * GetFeaturesP2PCacheCUDA / _IndexP2PCacheKernel (feature_ops.cu:38-138).
+ * Rows are raw bytes (row_bytes = stride * element size), so any dtype works.
+ * algo: 0 = auto, 1 = vectorised LDG/STG gather, 2 = TMA bulk (cp.async.bulk) staged gather. */
+int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids, int64_t n,
+                     void *out, int algo, void *stream);
+/* cached gather: row i comes from peer shard feat[dev][idx] when nids[i] hits the location
+ * table, else from host_table[nids[i]] (pinned / registered host memory, may be NULL when every
+ * id is cached). */
+int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_table, int64_t row_bytes,
+                    const void *loc_table, int64_t capacity, int itype, const void *nids,
+                    int64_t n, void *out, int algo, void *stream);
+
+/* ------------------------------------------------------------------ sub-CSR extraction
+ * replaces ExtractIndptr / ExtractEdgeData (src/sampling/cuda/utils.cu:12-101).
+ * indptr / edge_data may be device or mapped host memory. */
+int64_t dgs_extract_indptr_ws_bytes(int64_t n); /* scan_ws size; first 256 bytes zero on entry */
+int dgs_extract_indptr(int itype, int etype, const void *nids, int64_t n, const void *indptr,
+                       void *sub_indptr /* n+1 */, void *scan_ws, void *stream);
+int dgs_extract_edge_data(int itype, int etype, int elem_bytes, const void *nids, int64_t n,
+                          const void *indptr, const void *sub_indptr, const void *edge_data,
+                          void *sub_edge_data, void *stream);
+
+/* ------------------------------------------------------------------ sampling
+ * replaces RowWiseSampling{Uniform,Bias}CUDA (src/sampling/cuda/rowwise_sampling.cu:143-189,
+ * rowwise_sampling_bias.cu:226-288) and the ...WithP2PCachingCUDA variants
+ * (rowwise_sampling_p2p.cu:142-270, rowwise_sampling_bias_p2p.cu:227-385).
+ *
+ * Graph source description (where a seed's CSR row lives). */
+typedef struct {
+  int itype;                 /* ids: seeds / indices / outputs */
+  int etype;                 /* indptr */
+  /* un-cached source (plain ops, and the miss path of the cached sampler): device or mapped
+   * host memory, indexed by global node id.  probs NULL => uniform. */
+  const void *indptr;
+  const void *indices;
+  const float *probs;
+  /* cached shards (NULL => plain op).  Shard-local CSR: indptr[local idx], indices, probs. */
+  const dgs_p2p_server_t *p2p_indptr;
+  const dgs_p2p_server_t *p2p_indices;
+  const dgs_p2p_server_t *p2p_probs;
+  const void *loc_table;
+  int64_t loc_capacity;
+} dgs_graph_t;
+
+/* Workspace size (bytes) for a call over at most max_seeds seeds.  The first 256 bytes must be
+ * zero on entry (they are left zero on exit). */
+int64_t dgs_sample_ws_bytes(int64_t max_seeds);
+
+/* One hop.  seeds: device ids; num_seeds_dev: optional device int64 holding the live seed count
+ * (NULL => num_seeds is exact); num_seeds is then the upper bound used for grids / capacity.
+ * num_picks < 0 => every neighbour (DGL convention; the reference has no such mode, it is
+ * emulated there with num_picks >= max degree).
+ * Outputs: out_row / out_col (capacity out_capacity entries, seed-major, CSR order on the copy
+ * path, exactly the reference's layout), out_nnz_dev (device int64).  When out_capacity is
+ * too small the call still counts (nnz is exact) and skips the seeds whose output would not fit
+ * (the host re-runs with the exact size - the same result, RNG is counter based). */
+int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                         const int64_t *num_seeds_dev, int64_t num_picks, int replace,
+                         uint64_t rng_seed, void *out_row, void *out_col, int64_t out_capacity,
+                         int64_t *out_nnz_dev, void *ws, void *stream);
+
+/* Whole mini-batch: num_layers hops (fan_out walked from the back, like the reference's
+ * sampler.cc:20 and DGL), each hop sampled and relabelled (in place: out_row / out_col come back
+ * as positions in out_frontier[l]); hop l+1's seeds are hop l's frontier.  Everything is enqueued
+ * with device-side counts; the caller reads counts_dev = {nnz_0, |frontier_0|, nnz_1, ...} (2 L
+ * int64) once at the end.  Replaces P2PCacheNodeClassificationSample{Uniform,Bias}
+ * (src/sampling/sampler.cc:14-62).  Capacities: cap_edges[l] >= ub_l * k_l,
+ * cap_frontier[l] >= ub_l * (1 + k_l) with ub_0 = num_seeds, ub_{l+1} = ub_l * (1 + k_l);
+ * relabel_capacity >= 2 * max_l ub_{l+1}. */
+int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds, int num_layers,
+                      const int64_t *fan_out, int replace, uint64_t rng_seed,
+                      void *const *out_frontier, void *const *out_row, void *const *out_col,
+                      const int64_t *cap_edges, const int64_t *cap_frontier, int64_t *counts_dev,
+                      void *sample_ws, void *relabel_table, int64_t relabel_capacity,
+                      void *relabel_ws, void *stream);
+
+/* ------------------------------------------------------------------ relabel
+ * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):
+ * unique = first-occurrence-order unique of the concatenation of the mapping parts, every id of
+ * the relabel parts is replaced by its position in `unique` (-1 if absent); rel_out[p] has the
+ * shape of rel_ptrs[p].  Up to 4 parts on each side (no torch::cat needed); *_counts are exact
+ * lengths or, when the matching *_counts_dev[p] (device int64) is non-NULL, upper bounds with the
+ * live length on the device - this lets a whole multi-hop batch be enqueued with no host sync.
+ * table: capacity x 16 B slots, capacity a power of two >= 2 * sum(map_counts), all-0xFF on entry
+ * and restored to all-0xFF on exit (a persistent table never needs a memset).
+ * ws: dgs_relabel_ws_bytes(sum(map_counts)) bytes whose first 256 bytes are zero on entry (they
+ * are left zero on exit).  num_unique_dev: device int64. */
+int64_t dgs_relabel_table_capacity(int64_t n);
+int64_t dgs_relabel_table_bytes(int64_t n);
+int64_t dgs_relabel_ws_bytes(int64_t n);
+int dgs_relabel(int itype, int n_map, const void *const *map_ptrs, const int64_t *map_counts,
+                const int64_t *const *map_counts_dev, int n_rel, const void *const *rel_ptrs,
+                const int64_t *rel_counts, const int64_t *const *rel_counts_dev,
+                void *const *rel_out, void *unique_out, int64_t *num_unique_dev, void *table,
+                int64_t capacity, void *ws, void *stream);
+
+/* ------------------------------------------------------------------ cache-policy heat
+ * replaces ComputeFrontierHeat{,WithBias} (src/cache/cuda/preprocess_heat.cu:14-121). */
+int dgs_frontier_heat(int itype, int etype, const void *seeds, int64_t n, const void *indptr,
+                      const void *indices, const float *probs, const float *seeds_heat,
+                      float *frontier_heat, int64_t num_picks, int64_t indptr_diff, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGS_B200_H_ */

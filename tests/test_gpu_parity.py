@@ -1,0 +1,568 @@
+"""GPU: the sm_100a path (through the C-ABI, via the dgs plugin API) against the CPU oracle.
+
+Bit-exact: extract / index_select, location-table lookups, sub-CSR extraction, full-neighbour
+sampling, relabel, multi-hop blocks on the copy path.  Random sampling: validity, no duplicates
+without replacement, exact counts, reproducibility, and chi-square tests (tolerance stated in
+each test)."""
+import numpy as np
+import pytest
+import torch
+
+import dgs_synth
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def small_graph(N=3000, E=60000, seed=0, weights=False, dtype=torch.int64):
+    indptr, indices, probs = dgs_synth.make_csr(N, E, seed=seed, weights=weights, id_dtype=dtype)
+    return indptr, indices, probs
+
+
+# ------------------------------------------------------------------ extract
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("dim,dtype", [(100, torch.float32), (128, torch.float32),
+                                       (256, torch.bfloat16), (4, torch.float32),
+                                       (36, torch.int64)])
+def test_index_select_bit_exact(dgs, cuda, algo, dim, dtype):
+    N, R = 20000, 70001
+    ids = torch.arange(N)
+    feat = dgs_synth.feature_rows(ids, dim, dtype if dtype != torch.int64 else torch.int64)
+    g = torch.Generator().manual_seed(dim)
+    nids = torch.randint(0, N, (R,), generator=g)
+    out = dgs.ops._CAPI_cuda_index_select(feat.to(cuda), nids.to(cuda), algo)
+    assert out.shape == (R, dim) and out.dtype == feat.dtype
+    exp = oracle.index_select(t2n(feat.view(torch.int16) if dtype == torch.bfloat16 else feat), t2n(nids))
+    got = t2n(out.view(torch.int16) if dtype == torch.bfloat16 else out)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("dim,dtype", [(1, torch.int64), (1, torch.float32), (10, torch.float32),
+                                       (3, torch.int32), (7, torch.float16)])
+def test_index_select_unaligned_rows(dgs, cuda, dim, dtype):
+    """row sizes that are not multiples of 16 bytes, 1-D tables (labels), int ids of both widths.
+    (The reference's 1-D path truncates floats through an integer temp, feature_ops.cu:26-34 -
+    a bug; we return the values unchanged.)"""
+    N, R = 999, 5003
+    g = torch.Generator().manual_seed(3)
+    if dtype.is_floating_point:
+        table = torch.randn(N, dim, generator=g).to(dtype)
+    else:
+        table = torch.randint(-1000, 1000, (N, dim), generator=g, dtype=dtype)
+    if dim == 1:
+        table = table.reshape(N)
+    for idt in (torch.int64, torch.int32):
+        nids = torch.randint(0, N, (R,), generator=g).to(idt)
+        out = dgs.ops._CAPI_cuda_index_select(table.to(cuda), nids.to(cuda))
+        assert out.shape == (R,) + tuple(table.shape[1:])
+        assert torch.equal(out.cpu(), table[nids.long()])
+
+
+def test_index_select_edge_cases(dgs, cuda):
+    feat = torch.arange(100).float().reshape(10, 10)
+    empty = dgs.ops._CAPI_cuda_index_select(feat.to(cuda), torch.empty(0, dtype=torch.int64, device=cuda))
+    assert empty.shape == (0, 10)
+    one = dgs.ops._CAPI_cuda_index_select(feat.to(cuda), torch.tensor([9], device=cuda))
+    assert torch.equal(one.cpu(), feat[9:10])
+    # repeated ids, pinned-host table (labels path of the training loop, node_classification.py:228)
+    pinned = feat.pin_memory()
+    nids = torch.tensor([7, 7, 0, 9, 7] * 50, device=cuda)
+    out = dgs.ops._CAPI_cuda_index_select(pinned, nids)
+    assert torch.equal(out.cpu(), feat[nids.cpu()])
+    with pytest.raises(RuntimeError, match="neither pinned"):
+        dgs.ops._CAPI_cuda_index_select(feat, nids)
+    with pytest.raises(RuntimeError, match="int32 or int64"):
+        dgs.ops._CAPI_cuda_index_select(feat.to(cuda), nids.to(torch.int16))
+
+
+def test_index_select_3d_table(dgs, cuda):
+    table = torch.arange(6 * 4 * 5, dtype=torch.float32).reshape(6, 4, 5)
+    nids = torch.tensor([5, 0, 3], device=cuda)
+    out = dgs.ops._CAPI_cuda_index_select(table.to(cuda), nids)
+    assert out.shape == (3, 4, 5) and torch.equal(out.cpu(), table[nids.cpu()])
+
+
+# ------------------------------------------------------------------ location table + cached extract
+def _virtual_feature_setup(dgs, cuda, N, D, P, per, seed, dtype=torch.float32):
+    rng = np.random.default_rng(seed)
+    feat = dgs_synth.feature_rows(torch.arange(N), D, dtype)
+    lists = [np.sort(rng.choice(N, per, replace=False)) for _ in range(P)]
+    shards = [feat[torch.from_numpy(l)].to(cuda) for l in lists]
+    return feat, lists, shards
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_loc_table_lookup_matches_oracle(dgs, cuda, P):
+    from dgs import _lib
+    from dgs._util import ptr, stream
+    lib = _lib.lib()
+    N, per = 50000, 6000
+    rng = np.random.default_rng(P)
+    lists = [rng.choice(N, per, replace=False) for _ in range(P)]
+    n_unique = len(np.unique(np.concatenate(lists)))
+    cap = lib.dgs_loc_table_capacity(n_unique)
+    assert cap == oracle.hashmap_capacity(n_unique)
+    q = rng.integers(0, N, 30000)
+    dl = [torch.from_numpy(l).to(cuda) for l in lists]
+    qd = torch.from_numpy(q).to(cuda)
+    for rank in range(P):
+        table = torch.empty(2 * cap, dtype=torch.int64, device=cuda)
+        _lib.check(lib.dgs_loc_table_build(ptr(table), cap, 1, P, rank,
+                                           _lib.vp_array([ptr(t) for t in dl]),
+                                           _lib.i64_array([per] * P), stream()))
+        od = torch.empty_like(qd)
+        oi = torch.empty_like(qd)
+        _lib.check(lib.dgs_loc_table_lookup(ptr(table), cap, 1, ptr(qd), len(q), ptr(od), ptr(oi), stream()))
+        key, idx, dev = oracle.hashmap_build(lists, rank, n_unique)
+        ed, ei = oracle.hashmap_lookup(key, idx, dev, q)
+        assert np.array_equal(t2n(od), ed) and np.array_equal(t2n(oi), ei)
+        # unpacked (key, idx, devid) tensors hold the same set of entries as the reference layout
+        k2 = torch.empty(cap, dtype=torch.int64, device=cuda)
+        i2 = torch.empty_like(k2)
+        d2 = torch.empty_like(k2)
+        _lib.check(lib.dgs_loc_table_unpack(ptr(table), cap, 1, ptr(k2), ptr(i2), ptr(d2), stream()))
+        ours = sorted(zip(t2n(k2)[t2n(k2) >= 0].tolist(), t2n(d2)[t2n(k2) >= 0].tolist(), t2n(i2)[t2n(k2) >= 0].tolist()))
+        refs = sorted(zip(key[key >= 0].tolist(), dev[key >= 0].tolist(), idx[key >= 0].tolist()))
+        assert ours == refs
+        assert (t2n(i2)[t2n(k2) < 0] == -1).all() and (t2n(d2)[t2n(k2) < 0] == -1).all()
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("P,rank", [(1, 0), (2, 1), (4, 2), (8, 7)])
+def test_extract_p2p_virtual_ranks_bit_exact(dgs, cuda, P, rank, algo):
+    """Multi-rank cached extract emulated on one GPU: every emulated rank's shard is a tensor of this
+    process, the location table is built from rank `rank`'s point of view (local wins)."""
+    from dgs import _lib
+    from dgs._util import ptr, stream
+    lib = _lib.lib()
+    N, D, per = 30000, 100, 3000
+    feat, lists, shards = _virtual_feature_setup(dgs, cuda, N, D, P, per, seed=10 * P + rank)
+    server = dgs.classes.TensorP2PServer._virtual(shards, rank)
+    n_unique = len(np.unique(np.concatenate(lists)))
+    cap = lib.dgs_loc_table_capacity(n_unique)
+    table = torch.empty(2 * cap, dtype=torch.int64, device=cuda)
+    dl = [torch.from_numpy(l).to(cuda) for l in lists]
+    _lib.check(lib.dgs_loc_table_build(ptr(table), cap, 1, P, rank, _lib.vp_array([ptr(t) for t in dl]),
+                                       _lib.i64_array([per] * P), stream()))
+    q = torch.randint(0, N, (40000,), generator=torch.Generator().manual_seed(1))
+    host = feat.pin_memory()
+    out = torch.empty((len(q), D), dtype=feat.dtype, device=cuda)
+    qd = q.to(cuda)
+    if algo == 2:
+        # TMA variant is only selected when every source is device memory: restrict to cached ids
+        cached = torch.from_numpy(np.unique(np.concatenate(lists)))
+        q = cached[torch.randint(0, len(cached), (40000,), generator=torch.Generator().manual_seed(2))]
+        qd = q.to(cuda)
+    _lib.check(lib.dgs_extract_p2p(server._handle, ptr(host), D * 4, ptr(table), cap, 1, ptr(qd), len(q),
+                                   ptr(out), algo, stream()))
+    key, idx, dev = oracle.hashmap_build(lists, rank, n_unique)
+    exp = oracle.extract_p2p(t2n(feat), [t2n(s) for s in shards], key, idx, dev, t2n(q))
+    assert np.array_equal(t2n(out), exp)
+    assert np.array_equal(t2n(out), t2n(feat)[t2n(q)])
+
+
+def test_feature_server_reference_test_input(dgs, cuda):
+    """tests/test_feature_server.py:20-52 with one rank (cache [0, 3], misses from pinned host)."""
+    feature = torch.arange(0, 100, 1).float().pin_memory().reshape(10, 10)
+    fs = dgs.classes.P2PCacheFeatureServer(feature, torch.tensor([0, 3]).to(cuda), 0)
+    assert torch.equal(fs._CAPI_get_cpu_feature(), feature)
+    assert torch.equal(fs._CAPI_get_gpu_feature().cpu(), feature[[0, 3]])
+    out = fs._CAPI_get_feature(torch.tensor([0, 3, 5, 7]).to(cuda))
+    assert out.shape == (4, 10)
+    assert torch.equal(out.cpu(), feature[[0, 3, 5, 7]])
+    key, idx, dev = fs._CAPI_get_local_cache_hashmap_tensors()
+    assert key.numel() == 8 and sorted(key[key >= 0].tolist()) == [0, 3]
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        fs._CAPI_get_feature(torch.tensor([0]))
+
+
+@pytest.mark.parametrize("ratio", [0.01, 0.25, 1.0])
+def test_feature_server_cache_ratio(dgs, cuda, ratio):
+    N, D = 20000, 100
+    feat = dgs_synth.feature_rows(torch.arange(N), D).pin_memory()
+    g = torch.Generator().manual_seed(7)
+    cache = torch.randperm(N, generator=g)[:max(1, int(N * ratio))]
+    fs = dgs.classes.P2PCacheFeatureServer(feat, cache, 0)
+    q = torch.randint(0, N, (50000,), generator=g)
+    out = fs._CAPI_get_feature(q.to(cuda))
+    assert torch.equal(out.cpu(), feat[q])
+    key, idx, dev = oracle.hashmap_build([t2n(cache)], 0)
+    exp = oracle.extract_p2p(t2n(feat), [t2n(feat[cache])], key, idx, dev, t2n(q))
+    assert np.array_equal(t2n(out), exp)
+
+
+# ------------------------------------------------------------------ sub-CSR extraction
+def test_extract_indptr_edge_data_kat(dgs, cuda):
+    """tests/test_extract.py:5-18"""
+    indptr = torch.tensor([0, 4, 5, 5, 5, 5, 10, 10, 10, 10, 10, 10]).to(cuda)
+    indices = torch.tensor([1, 2, 3, 4, 5, 6, 7, 8, 9, 10]).to(cuda)
+    probs = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5, 0.1, 0.2, 0.3, 0.4, 0.5]).to(cuda)
+    nids = torch.tensor([0, 1, 5]).to(cuda)
+    sub = dgs.ops._Test_ExtractIndptr(nids, indptr)
+    assert sub.tolist() == [0, 4, 5, 10]
+    assert dgs.ops._Test_ExtractEdgeData(nids, indptr, sub, indices).tolist() == list(range(1, 11))
+    assert torch.equal(dgs.ops._Test_ExtractEdgeData(nids, indptr, sub, probs), probs)
+
+
+@pytest.mark.parametrize("src", ["cuda", "pinned"])
+def test_extract_subcsr_random(dgs, cuda, src):
+    indptr, indices, probs = small_graph(30000, 700000, seed=2, weights=True)
+    g = torch.Generator().manual_seed(0)
+    nids = torch.randperm(30000, generator=g)[:9000]
+    put = (lambda t: t.to(cuda)) if src == "cuda" else (lambda t: t.pin_memory())
+    ip, ix, pr = put(indptr), put(indices), put(probs)
+    sub = dgs.ops._Test_ExtractIndptr(nids.to(cuda), ip)
+    exp_sub = oracle.extract_indptr(t2n(nids), t2n(indptr))
+    assert np.array_equal(t2n(sub), exp_sub)
+    got_i = dgs.ops._Test_ExtractEdgeData(nids.to(cuda), ip, sub, ix)
+    got_p = dgs.ops._Test_ExtractEdgeData(nids.to(cuda), ip, sub, pr)
+    assert np.array_equal(t2n(got_i), oracle.extract_edge_data(t2n(nids), t2n(indptr), exp_sub, t2n(indices)))
+    assert np.array_equal(t2n(got_p), oracle.extract_edge_data(t2n(nids), t2n(indptr), exp_sub, t2n(probs)))
+    # int32 everything
+    sub32 = dgs.ops._Test_ExtractIndptr(nids.int().to(cuda), put(indptr.int()))
+    assert sub32.dtype == torch.int32 and np.array_equal(t2n(sub32), exp_sub)
+
+
+# ------------------------------------------------------------------ full-neighbour sampling (bit-exact)
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("mode", ["minus1", "k>=maxdeg"])
+def test_sample_all_neighbors_bit_exact(dgs, cuda, idt, mode):
+    indptr, indices, _ = small_graph(5000, 120000, seed=1, dtype=idt)
+    maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    g = torch.Generator().manual_seed(0)
+    seeds = torch.randint(0, 5000, (3000,), generator=g).to(idt)
+    k = -1 if mode == "minus1" else maxdeg + 3
+    ip = indptr.to(idt).to(cuda)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(seeds.to(cuda), ip, indices.to(cuda), k, False)
+    er, ec = oracle.sample_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices))
+    assert row.dtype == idt and col.dtype == idt
+    assert np.array_equal(t2n(row), er) and np.array_equal(t2n(col), ec)
+    # biased op, copy path: identical
+    w = torch.rand(indices.numel()) + 0.1
+    row2, col2 = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds.to(cuda), ip, indices.to(cuda), w.to(cuda), k, False)
+    assert torch.equal(row2, row) and torch.equal(col2, col)
+
+
+def test_sample_pinned_host_graph(dgs, cuda):
+    """indptr / indices in pinned host memory, read through UVA (scripts/ncu_sampling.py:9-26)."""
+    indptr, indices, _ = small_graph(2000, 30000, seed=4)
+    seeds = torch.arange(0, 2000, 3)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(seeds.to(cuda), indptr.pin_memory(), indices.pin_memory(), -1, False)
+    er, ec = oracle.sample_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices))
+    assert np.array_equal(t2n(row), er) and np.array_equal(t2n(col), ec)
+
+
+def test_sample_empty_and_isolated(dgs, cuda):
+    indptr = torch.tensor([0, 0, 0, 3, 3]).to(cuda)
+    indices = torch.tensor([1, 0, 3]).to(cuda)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(torch.empty(0, dtype=torch.int64, device=cuda), indptr, indices, 2, False)
+    assert row.numel() == 0 and col.numel() == 0
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(torch.tensor([0, 1, 3]).to(cuda), indptr, indices, 2, False)
+    assert row.numel() == 0
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(torch.tensor([0, 2, 3]).to(cuda), indptr, indices, 5, True)
+    assert row.tolist() == [2] * 5 and set(col.tolist()) <= {0, 1, 3}
+
+
+# ------------------------------------------------------------------ random sampling properties
+def _check_sample(seeds, indptr, indices, row, col, k, replace):
+    seeds, indptr, indices, row, col = map(t2n, (seeds, indptr, indices, row, col))
+    o = 0
+    for s in seeds:
+        nb = indices[indptr[s]:indptr[s + 1]]
+        d = len(nb)
+        c = (k if d > 0 else 0) if replace else min(d, k)
+        assert (row[o:o + c] == s).all()
+        got = col[o:o + c]
+        if not replace and d <= k:
+            assert got.tolist() == nb.tolist()          # copy path, CSR order
+        else:
+            pool = {}
+            for v in nb.tolist():
+                pool[v] = pool.get(v, 0) + 1
+            cnt = {}
+            for v in got.tolist():
+                assert v in pool                           # valid neighbour
+                cnt[v] = cnt.get(v, 0) + 1
+            if not replace:                                # no duplicate *edge* picked
+                assert all(cnt[v] <= pool[v] for v in cnt)
+        o += c
+    assert o == len(row) == len(col)
+
+
+@pytest.mark.parametrize("k", [1, 5, 15, 25, 32, 33, 70])
+@pytest.mark.parametrize("replace", [False, True])
+def test_uniform_sampling_properties(dgs, cuda, k, replace):
+    indptr, indices, _ = small_graph(4000, 100000, seed=3)
+    seeds = torch.randperm(4000, generator=torch.Generator().manual_seed(k))[:1500]
+    args = (seeds.to(cuda), indptr.to(cuda), indices.to(cuda), k, replace)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(*args, rng_seed=123)
+    _check_sample(seeds, indptr, indices, row, col, k, replace)
+    row2, col2 = dgs.ops._CAPI_cuda_sample_neighbors(*args, rng_seed=123)
+    assert torch.equal(col, col2)                          # same seed -> same sample
+    row3, col3 = dgs.ops._CAPI_cuda_sample_neighbors(*args, rng_seed=124)
+    assert not torch.equal(col, col3)
+
+
+@pytest.mark.parametrize("k", [1, 10, 25, 32, 40])
+@pytest.mark.parametrize("replace", [False, True])
+def test_biased_sampling_properties(dgs, cuda, k, replace):
+    indptr, indices, probs = small_graph(4000, 100000, seed=5, weights=True)
+    seeds = torch.randperm(4000, generator=torch.Generator().manual_seed(k))[:1500]
+    args = (seeds.to(cuda), indptr.to(cuda), indices.to(cuda), probs.to(cuda), k, replace)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(*args, rng_seed=9)
+    _check_sample(seeds, indptr, indices, row, col, k, replace)
+    row2, col2 = dgs.ops._CAPI_cuda_sample_neighbors_bias(*args, rng_seed=9)
+    assert torch.equal(col, col2)
+
+
+def _star_graph(deg, copies, cuda, weights=None):
+    """`copies` seeds, each with the same `deg` distinct neighbours 0..deg-1 -> per-position counts."""
+    indptr = torch.arange(0, (copies + 1) * deg, deg)
+    indices = torch.arange(deg).repeat(copies)
+    w = None if weights is None else weights.repeat(copies)
+    return indptr.to(cuda), indices.to(cuda), None if w is None else w.to(cuda)
+
+
+def _chi2(counts, expected):
+    return float(((counts - expected) ** 2 / expected).sum())
+
+
+@pytest.mark.parametrize("deg,k", [(10, 3), (40, 15), (200, 25), (33, 32)])
+def test_uniform_without_replacement_is_uniform(dgs, cuda, deg, k):
+    """Inclusion frequency of every neighbour position must be k/deg.  Chi-square over `deg` cells
+    against the exact expectation; threshold = df + 6*sqrt(2*df) (about 6 sigma of the chi-square
+    distribution, false-alarm rate < 1e-6)."""
+    copies = 20000
+    indptr, indices, _ = _star_graph(deg, copies, cuda)
+    seeds = torch.arange(copies, device=cuda)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(seeds, indptr, indices, k, False, rng_seed=77)
+    assert col.numel() == copies * k
+    counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    exp = copies * k / deg
+    # inclusion indicators are Bernoulli(p): variance exp*(1-p); normalise so that chi2 ~ chi2(df)
+    p = k / deg
+    chi2 = _chi2(counts, exp) / (1 - p) * (deg - 1) / deg
+    df = deg - 1
+    assert chi2 < df + 6 * np.sqrt(2 * df), (chi2, df)
+    # and no duplicates inside a seed
+    per_seed = col.reshape(copies, k).sort(dim=1).values
+    assert (per_seed[:, 1:] != per_seed[:, :-1]).all()
+
+
+@pytest.mark.parametrize("deg,k", [(10, 4), (100, 20)])
+def test_uniform_with_replacement_is_uniform(dgs, cuda, deg, k):
+    copies = 20000
+    indptr, indices, _ = _star_graph(deg, copies, cuda)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors(torch.arange(copies, device=cuda), indptr, indices, k, True, rng_seed=5)
+    counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    df = deg - 1
+    assert _chi2(counts, copies * k / deg) < df + 6 * np.sqrt(2 * df)
+
+
+@pytest.mark.parametrize("deg", [8, 50, 300])
+def test_biased_k1_and_replace_follow_weights(dgs, cuda, deg):
+    """k = 1 without replacement and any k with replacement must pick edge i with probability
+    w_i / sum(w) exactly.  Chi-square against the weights, 6-sigma bound."""
+    copies = 30000
+    g = torch.Generator().manual_seed(deg)
+    w = (torch.rand(deg, generator=g) * 3 + 0.05).float()
+    indptr, indices, probs = _star_graph(deg, copies, cuda, w)
+    seeds = torch.arange(copies, device=cuda)
+    pw = (w / w.sum()).double().numpy()
+    df = deg - 1
+    bound = df + 6 * np.sqrt(2 * df)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds, indptr, indices, probs, 1, False, rng_seed=3)
+    counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    assert _chi2(counts, copies * pw) < bound
+    for k in (1, 7):
+        row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds, indptr, indices, probs, k, True, rng_seed=4 + k)
+        counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+        assert _chi2(counts, copies * k * pw) < bound
+
+
+def test_biased_without_replacement_matches_ares_reference(dgs, cuda):
+    """k > 1: A-Res inclusion probabilities are not proportional to the weights (only the first draw
+    is); compare with the CPU A-Res restatement of the oracle (two-sample chi-square, 6 sigma)."""
+    deg, k, copies = 12, 4, 40000
+    w = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5, 0.1, 0.2, 0.3, 0.4, 0.5, 2.0, 3.0])
+    indptr, indices, probs = _star_graph(deg, copies, cuda, w)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(torch.arange(copies, device=cuda), indptr, indices, probs, k, False, rng_seed=1)
+    a = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    r2, c2 = oracle.cpu_sample_neighbors(np.arange(copies), t2n(indptr), t2n(indices), t2n(probs), k, 99)
+    b = np.bincount(c2, minlength=deg).astype(np.float64)
+    chi2 = float(((a - b) ** 2 / (a + b)).sum())
+    df = deg - 1
+    assert chi2 < df + 6 * np.sqrt(2 * df), chi2
+    per_seed = col.reshape(copies, k).sort(dim=1).values
+    assert (per_seed[:, 1:] != per_seed[:, :-1]).all()
+
+
+# ------------------------------------------------------------------ relabel (bit-exact)
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+def test_relabel_bit_exact(dgs, cuda, idt):
+    g = torch.Generator().manual_seed(0)
+    for n_seed, n_col, space in [(3, 9, 11), (1024, 5000, 3000), (5000, 200000, 50000), (10, 300000, 2449029)]:
+        seeds = torch.randperm(space, generator=g)[:n_seed].to(idt)
+        col = torch.randint(0, space, (n_col,), generator=g).to(idt)
+        row = seeds[torch.randint(0, n_seed, (n_col,), generator=g)]
+        uniq, (rrow, rcol) = dgs.ops._CAPI_cuda_sampled_tensor_relabel([seeds.to(cuda), col.to(cuda)], [row.to(cuda), col.to(cuda)])
+        eu, (er, ec) = oracle.relabel([t2n(seeds), t2n(col)], [t2n(row), t2n(col)])
+        assert uniq.dtype == idt
+        assert np.array_equal(t2n(uniq), eu) and np.array_equal(t2n(rrow), er) and np.array_equal(t2n(rcol), ec)
+
+
+def test_relabel_absent_keys_and_many_parts(dgs, cuda):
+    a = torch.tensor([5, 7, 5, 9]).to(cuda)
+    parts = [a, torch.tensor([1, 7]).to(cuda), torch.tensor([2]).to(cuda), torch.tensor([9, 3]).to(cuda), torch.tensor([4, 4]).to(cuda)]
+    q = torch.tensor([[9, 100], [4, 5]]).to(cuda)
+    uniq, (rq,) = dgs.ops._CAPI_cuda_sampled_tensor_relabel(parts, [q])
+    assert uniq.tolist() == [5, 7, 9, 1, 2, 3, 4]
+    assert rq.tolist() == [[2, -1], [6, 0]]
+    # the reference test graph
+    uniq, (rr, rc) = dgs.ops._CAPI_cuda_sampled_tensor_relabel(
+        [torch.tensor([0, 3, 5]).to(cuda), torch.tensor([1, 2, 3, 4, 6, 7, 8, 9, 10]).to(cuda)],
+        [torch.tensor([0, 0, 0, 0, 5, 5, 5, 5, 5]).to(cuda), torch.tensor([1, 2, 3, 4, 6, 7, 8, 9, 10]).to(cuda)])
+    assert uniq.tolist() == [0, 3, 5, 1, 2, 4, 6, 7, 8, 9, 10]
+    assert rr.tolist() == [0, 0, 0, 0, 2, 2, 2, 2, 2] and rc.tolist() == [3, 4, 1, 5, 6, 7, 8, 9, 10]
+
+
+# ------------------------------------------------------------------ sampler class
+def _make_sampler(dgs, cuda, indptr, indices, probs, cache):
+    ip, ix = indptr.pin_memory(), indices.pin_memory()
+    pr = probs.pin_memory() if probs is not None else torch.Tensor()
+    return dgs.classes.P2PCacheSampler(ip, ix, pr, cache, 0), ip, ix
+
+
+def test_sampler_build_reference_test_input(dgs, cuda):
+    """tests/test_build_sampler.py:17-44 from rank 1's cache set, one rank."""
+    indptr = torch.tensor([0, 4, 5, 5, 5, 5, 10, 10, 10, 10, 10, 10])
+    indices = torch.tensor([1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+    probs = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5, 0.1, 0.2, 0.3, 0.4, 0.5])
+    s, ip, ix = _make_sampler(dgs, cuda, indptr, indices, probs, torch.tensor([3, 5]))
+    a, b, c = s._CAPI_get_cpu_structure_tensors()
+    assert a is ip and b is ix and torch.equal(c, probs)
+    li, lx, lp = s._CAPI_get_local_cache_structure_tensors()
+    assert li.tolist() == [0, 0, 5] and lx.tolist() == [6, 7, 8, 9, 10]
+    assert torch.equal(lp.cpu(), probs[5:])
+    key, idx, dev = s._CAPI_get_local_cache_hashmap_tensors()
+    assert key.numel() == 8                      # 2 * _UpPower(2)
+    ent = sorted(zip(key[key >= 0].tolist(), idx[key >= 0].tolist(), dev[key >= 0].tolist()))
+    assert ent == [(3, 0, 0), (5, 1, 0)]
+
+
+def test_sampler_uniform_reference_test_input(dgs, cuda):
+    """tests/test_sampler_uniform.py:14-38, one rank."""
+    indptr = torch.tensor([0, 4, 5, 5, 5, 5, 10, 10, 10, 10, 10, 10])
+    indices = torch.tensor([1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+    s, _, _ = _make_sampler(dgs, cuda, indptr, indices, None, torch.tensor([0, 3]))
+    out = s._CAPI_sample_node_classifiction(torch.tensor([0, 3, 5]).to(cuda), [2, 2], False)
+    assert len(out) == 2
+    seeds, frontier, row, col = out[0]
+    assert seeds.tolist() == [0, 3, 5] and row.tolist() == [0, 0, 2, 2]
+    assert frontier[:3].tolist() == [0, 3, 5]
+    nb = frontier[col].tolist()
+    assert set(nb[:2]) <= {1, 2, 3, 4} and len(set(nb[:2])) == 2
+    assert set(nb[2:]) <= {6, 7, 8, 9, 10} and len(set(nb[2:])) == 2
+    seeds2, frontier2, row2, col2 = out[1]
+    assert torch.equal(seeds2, frontier)
+    # second hop: node 0 and 5 give 2 each, node 1 (if reached) gives [5], everything else nothing
+    exp = 4 + (1 if 1 in frontier.tolist() else 0)
+    assert row2.numel() == exp
+
+
+@pytest.mark.parametrize("bias", [False, True])
+@pytest.mark.parametrize("cache_frac", [0.02, 0.5, 1.0])
+def test_sampler_blocks_copy_path_bit_exact(dgs, cuda, bias, cache_frac):
+    """Multi-hop blocks with every fan-out >= max degree (the reference's way to ask for all
+    neighbours) through the fused whole-batch path, and with fan-out -1 through the per-hop path:
+    both must equal the oracle's layer loop bit for bit (sampler.cc:14-62)."""
+    N = 1500
+    indptr, indices, probs = small_graph(N, 9000, seed=11, weights=bias)
+    maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    g = torch.Generator().manual_seed(1)
+    cache = torch.randperm(N, generator=g)[:max(1, int(N * cache_frac))]
+    s, _, _ = _make_sampler(dgs, cuda, indptr, indices, probs, cache)
+    seeds = torch.randperm(N, generator=g)[:40]
+    exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), 2)
+    for fan in ([maxdeg, maxdeg], [-1, -1]):
+        if bias and fan[0] > 0 and maxdeg > 3000:
+            continue
+        out = s._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False)
+        assert len(out) == 2
+        for (s_, f_, r_, c_), (es, ef, er, ec) in zip(out, exp):
+            assert np.array_equal(t2n(s_), es) and np.array_equal(t2n(f_), ef)
+            assert np.array_equal(t2n(r_), er) and np.array_equal(t2n(c_), ec)
+    # repeated calls reuse the persistent relabel table: must stay clean
+    out2 = s._CAPI_sample_node_classifiction(seeds.to(cuda), [maxdeg, maxdeg], False)
+    assert np.array_equal(t2n(out2[1][1]), exp[1][1])
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_sampler_blocks_random_properties(dgs, cuda, bias):
+    N = 20000
+    indptr, indices, probs = small_graph(N, 500000, seed=12, weights=bias)
+    g = torch.Generator().manual_seed(2)
+    cache = torch.randperm(N, generator=g)[:5000]
+    s, _, _ = _make_sampler(dgs, cuda, indptr, indices, probs, cache)
+    seeds = torch.randperm(N, generator=g)[:1024]
+    fan = [15, 10, 5]
+    out = s._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False, rng_seed=5)
+    assert len(out) == 3
+    cur = seeds
+    for li, (s_, f_, r_, c_) in enumerate(out):
+        k = fan[len(fan) - 1 - li]
+        assert torch.equal(s_.cpu(), cur)
+        f = f_.cpu()
+        assert torch.equal(f[:len(cur)], cur)             # seeds come first (they are unique)
+        assert len(torch.unique(f)) == len(f)
+        row_g, col_g = cur[r_.cpu()], f[c_.cpu()]
+        # relabelled COO maps back to a valid sample of the hop
+        _check_sample(cur, indptr, indices, row_g, col_g, k, False)
+        # frontier = first-occurrence unique of cat(seeds, cols)
+        eu, _ = oracle.relabel([t2n(cur), t2n(col_g)], [])
+        assert np.array_equal(t2n(f), eu)
+        cur = f
+    again = s._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False, rng_seed=5)
+    assert all(torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) for a, b in zip(out, again))
+
+
+def test_p2p_server_single_rank(dgs, cuda):
+    t = torch.arange(24, dtype=torch.float32, device=cuda).reshape(6, 4)
+    srv = dgs.classes.TensorP2PServer(t)
+    loc = srv._CAPI_get_local_device_tensor()
+    assert loc.shape == (6, 4) and torch.equal(loc, t) and loc.data_ptr() != t.data_ptr()
+    flat = srv._CAPI_get_device_tensor(0)
+    assert flat.shape == (24,) and torch.equal(flat, t.reshape(-1))
+    with pytest.raises(RuntimeError):
+        srv._CAPI_get_device_tensor(1)
+    with pytest.raises(RuntimeError, match="> 0"):
+        dgs.classes.TensorP2PServer(torch.empty(0, 4, device=cuda))
+    srv.close()
+
+
+def test_frontier_heat_matches_oracle(dgs, cuda):
+    indptr, indices, probs = small_graph(3000, 60000, seed=6, weights=True)
+    seeds = torch.randperm(3000, generator=torch.Generator().manual_seed(0))[:500]
+    heat = torch.zeros(3000)
+    heat[seeds] = torch.rand(500) + 0.1
+    for pr in (None, probs):
+        if pr is None:
+            got = dgs.ops._CAPI_compute_frontier_heat(seeds.to(cuda), indptr.to(cuda), indices.to(cuda), heat.to(cuda), 10, 0)
+        else:
+            got = dgs.ops._CAPI_compute_frontier_heat_with_bias(seeds.to(cuda), indptr.to(cuda), indices.to(cuda), pr.to(cuda), heat.to(cuda), 10, 0)
+        exp = oracle.frontier_heat(t2n(seeds), t2n(indptr), t2n(indices), None if pr is None else t2n(pr), t2n(heat), 10, 0)
+        # float atomics: summation order differs -> tolerance 1e-4 relative
+        assert np.allclose(t2n(got), exp, rtol=1e-4, atol=1e-5)
+
+
+def test_pin_memory_roundtrip(dgs, cuda):
+    t = torch.arange(1000, dtype=torch.float32).reshape(100, 10).clone()
+    assert not t.is_pinned()
+    dgs.ops._CAPI_tensor_pin_memory(t)
+    out = dgs.ops._CAPI_cuda_index_select(t, torch.tensor([3, 99], device=cuda))
+    assert torch.equal(out.cpu(), t[[3, 99]])
+    dgs.ops._CAPI_tensor_unpin_memory(t)
