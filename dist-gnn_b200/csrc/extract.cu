@@ -87,7 +87,7 @@ gather_rows_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64
       for (int u = 0; u < kGatherUnroll; ++u) {
         uint32_t e = base + u * kGatherThreads;
         if (e < total) {
-          uint32_t r = __umulhi(e, vpr_magic);  // e / vpr, exact for e < 2^16 (host-checked)
+          uint32_t r = vpr == 1 ? e : __umulhi(e, vpr_magic);  // e / vpr, exact for e < 2^16
           uint32_t c = e - r * vpr;
           v[u] = ld_stream<VecT>(reinterpret_cast<const VecT *>(s_src[r]) + c);
         }

@@ -173,11 +173,30 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t key, uint64_t item, uint
   return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
 }
 
+// Write the k picked neighbours.  w_idx may alias the first 4 k bytes of ocol (global scratch
+// mode): chunks are processed from the top and every lane reads its position before any lane
+// writes, so an 8-byte ocol[j] only overwrites positions >= j that were already consumed.
+template <typename IdT>
+__device__ __forceinline__ void emit_picks(const IdT *__restrict__ row, const int *w_idx, int k,
+                                           int lane, IdT seed, IdT *orow, IdT *ocol) {
+  for (int j0 = ((k - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+    const int j = j0 + lane;
+    int p = 0;
+    if (j < k) p = w_idx[j];
+    __syncwarp();
+    if (j < k) {
+      ocol[j] = row[p];
+      orow[j] = seed;
+    }
+    __syncwarp();
+  }
+}
+
 template <typename IdT, typename ET, int MODE>
 __global__ void __launch_bounds__(kPickWarps * 32)
 pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
             const int64_t *__restrict__ num_seeds_dev, int64_t k64, uint64_t rng_key, SampleWs ws,
-            IdT *__restrict__ out_row, IdT *__restrict__ out_col, int64_t capacity) {
+            IdT *out_row, IdT *out_col, int64_t capacity, int gmem_scratch) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -187,7 +206,10 @@ pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
   // per-warp scratch: k ints (uniform) or k floats + k ints (biased)
   int *w_idx = nullptr;
   float *w_key = nullptr;
-  if (k > 0) {
+  // Scratch for the selection state: shared memory, or - when num_picks is too large for it - the
+  // seed's own k output slots (k * sizeof(IdT) >= k * 4 bytes each in out_row / out_col), which
+  // are rewritten with the final (seed, neighbour) pairs afterwards.
+  if (k > 0 && !gmem_scratch) {
     if (MODE == kUniform) {
       w_idx = reinterpret_cast<int *>(pick_smem) + (size_t)warp * k;
     } else if (MODE == kBias) {
@@ -211,6 +233,10 @@ pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
     if (off + cnt > capacity) continue;  // counting-only call (caller re-runs with a larger buffer)
     IdT *orow = out_row + off;
     IdT *ocol = out_col + off;
+    if (gmem_scratch && !copy_path) {
+      w_key = reinterpret_cast<float *>(orow);
+      w_idx = reinterpret_cast<int *>(ocol);
+    }
 
     if (copy_path) {
       // CSR-order copy, 4 independent loads in flight per lane
@@ -268,11 +294,7 @@ pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
             __syncwarp();
           }
         }
-        for (int j = lane; j < k; j += 32) {
-          ocol[j] = row[w_idx[j]];
-          orow[j] = seed;
-        }
-        __syncwarp();
+        emit_picks(row, w_idx, k, lane, seed, orow, ocol);
       }
     } else if (MODE == kBias) {
       const float *wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
@@ -334,11 +356,7 @@ pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
         }
       }
       __syncwarp();
-      for (int j = lane; j < k; j += 32) {
-        ocol[j] = row[w_idx[j]];
-        orow[j] = seed;
-      }
-      __syncwarp();
+      emit_picks(row, w_idx, k, lane, seed, orow, ocol);
     } else {  // kBiasReplace
       const float *wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
       // pass 1: total weight, with exactly the arithmetic of pass 2
@@ -401,9 +419,11 @@ static int launch_sample(const GraphSrc &g, const IdT *seeds, int64_t num_seeds,
   size_t smem = 0;
   if (k > 32 && mode == kUniform) smem = (size_t)kPickWarps * k * sizeof(int);
   if (k > 0 && mode == kBias) smem = (size_t)kPickWarps * k * 2 * sizeof(float);
-  DGS_REQUIRE(smem <= 200 * 1024, "sample_neighbors: num_picks=%lld needs %zu bytes of shared "
-              "memory per CTA (max 204800); use num_picks=-1 for full neighbourhoods",
-              (long long)k, smem);
+  int gmem_scratch = 0;
+  if (smem > 96 * 1024) {  // huge num_picks: keep the selection state in the output slots instead
+    smem = 0;
+    gmem_scratch = 1;
+  }
   int grid = grid_for(num_seeds, kPickWarps, 8);
 #define DGS_PICK(M)                                                                             \
   do {                                                                                          \
@@ -412,7 +432,7 @@ static int launch_sample(const GraphSrc &g, const IdT *seeds, int64_t num_seeds,
       DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem));                                             \
     kern<<<grid, kPickWarps * 32, smem, st>>>(g, seeds, num_seeds, num_seeds_dev, k, rng_seed,  \
-                                              ws, out_row, out_col, capacity);                  \
+                                              ws, out_row, out_col, capacity, gmem_scratch);    \
   } while (0)
   switch (mode) {
     case kUniform: DGS_PICK(kUniform); break;

@@ -9,6 +9,7 @@ from ._util import (check_cpu, check_cuda, contiguous, itype, ptr, stream, tenso
 
 lib = _lib.lib
 check = _lib.check
+MAX_FUSED_ELEMS = 1 << 28  # ids in the worst-case arena of the fused whole-batch path (2 GiB of int64)
 
 
 def _barrier():
@@ -209,8 +210,12 @@ class _BlockPipeline:
                 ubs.append(ub)
                 nnz_ubs.append(ub * k)
                 ub = ub + ub * k
-            self._reserve(max(ubs), ub)
             total = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
+            if total > MAX_FUSED_ELEMS:
+                # worst-case buffers would be unreasonable (huge fan-out used as "all neighbours"):
+                # size every hop exactly instead, at the price of a host sync per hop
+                return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
+            self._reserve(max(ubs), ub)
             arena = torch.empty(total, dtype=seeds.dtype, device=self._device)
             fr, rows, cols = [], [], []
             off = 0

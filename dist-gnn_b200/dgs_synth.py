@@ -98,9 +98,9 @@ def feature_rows(nids, dim, dtype=torch.float32, seed=0):
 
 
 def make_csr(num_nodes, target_edges, seed=0, device="cpu", id_dtype=torch.int64, weights=False,
-             chunk=1 << 26):
+             chunk=1 << 26, classes=13):
     """Full CSR on one device: (indptr int64[N+1], indices id_dtype[E], probs fp32[E] or None)."""
-    deg = degrees(num_nodes, target_edges, seed, device=device)
+    deg = degrees(num_nodes, target_edges, seed, classes=classes, device=device)
     indptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
     torch.cumsum(deg, 0, out=indptr[1:])
     del deg

@@ -21,9 +21,18 @@ def _load_reference():
     if not cands:
         return None
     import torch  # noqa: F401  (the extension links libtorch)
-    spec = importlib.util.spec_from_file_location("dgs", cands[0])
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    # The reference module is also called `dgs` and pybind's def_submodule() registers
+    # "dgs.classes" / "dgs.ops" through sys.modules: hide this repo's package while it loads.
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "dgs" or k.startswith("dgs.")}
+    try:
+        spec = importlib.util.spec_from_file_location("dgs", cands[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k in list(sys.modules):
+            if k == "dgs" or k.startswith("dgs."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
     return mod
 
 

@@ -481,16 +481,15 @@ def test_sampler_blocks_copy_path_bit_exact(dgs, cuda, bias, cache_frac):
     neighbours) through the fused whole-batch path, and with fan-out -1 through the per-hop path:
     both must equal the oracle's layer loop bit for bit (sampler.cc:14-62)."""
     N = 1500
-    indptr, indices, probs = small_graph(N, 9000, seed=11, weights=bias)
+    indptr, indices, probs = dgs_synth.make_csr(N, 9000, seed=11, weights=bias, classes=5)
     maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    assert maxdeg < 400
     g = torch.Generator().manual_seed(1)
     cache = torch.randperm(N, generator=g)[:max(1, int(N * cache_frac))]
     s, _, _ = _make_sampler(dgs, cuda, indptr, indices, probs, cache)
     seeds = torch.randperm(N, generator=g)[:40]
     exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), 2)
     for fan in ([maxdeg, maxdeg], [-1, -1]):
-        if bias and fan[0] > 0 and maxdeg > 3000:
-            continue
         out = s._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False)
         assert len(out) == 2
         for (s_, f_, r_, c_), (es, ef, er, ec) in zip(out, exp):
@@ -528,6 +527,29 @@ def test_sampler_blocks_random_properties(dgs, cuda, bias):
         cur = f
     again = s._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False, rng_seed=5)
     assert all(torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) for a, b in zip(out, again))
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_huge_num_picks_uses_output_scratch(dgs, cuda, bias):
+    """num_picks far beyond what shared memory holds (the reference asserts num_picks <= 32 for the
+    biased kernel, rowwise_sampling_bias.cu:73): rows above k are still sampled without
+    duplicates, rows below are copied; and the class API falls back to exactly-sized hops."""
+    N = 3000
+    indptr, indices, probs = dgs_synth.make_csr(N, 400000, seed=13, weights=True, classes=9)
+    deg = indptr[1:] - indptr[:-1]
+    k = 4000   # 8 warps * k * 4 (or 8) bytes > the 96 KiB shared-memory budget of the pick kernel
+    assert int((deg > k).sum()) >= 3
+    seeds = torch.argsort(deg, descending=True)[:64]
+    # distinct neighbour ids per row so "no duplicates" is checkable on ids
+    for s_ in seeds.tolist():
+        b, e = int(indptr[s_]), int(indptr[s_ + 1])
+        indices[b:e] = torch.arange(e - b) % N if e - b <= N else indices[b:e]
+    args = [seeds.to(cuda), indptr.to(cuda), indices.to(cuda)]
+    if bias:
+        row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(*args, probs.to(cuda), k, False, rng_seed=3)
+    else:
+        row, col = dgs.ops._CAPI_cuda_sample_neighbors(*args, k, False, rng_seed=3)
+    _check_sample(seeds, indptr, indices, row, col, k, False)
 
 
 def test_p2p_server_single_rank(dgs, cuda):
