@@ -280,6 +280,9 @@ def run_b200(args, fan_out):
         return float(t.item())
 
     # ---- device-resident timing ("value")
+    for i in range(2):   # set-up (allocator pools, lazily enabled peer mappings) - not a timed step
+        step_device(i)
+        step_e2e(i)
     for i in range(W):
         step_device(i)
     barrier()
@@ -308,9 +311,9 @@ def run_b200(args, fan_out):
     # are re-issued back to back on the same stream between two CUDA events, so the figure is the
     # kernel's own average duration (no host gaps); every launch gathers a different random
     # 75+ MB row set out of the 0.98 GB table into its own output buffer.
-    for f in frontiers[:min(3, K)]:
-        extract(f)
-    torch.cuda.synchronize()
+    outs = [extract(f) for f in frontiers]   # untimed pass: the caching allocator now owns K outputs
+    del outs
+    barrier()
     x0 = torch.cuda.Event(enable_timing=True)
     x1 = torch.cuda.Event(enable_timing=True)
     outs = []

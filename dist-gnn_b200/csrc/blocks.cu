@@ -1,0 +1,751 @@
+// blocks.cu - the fused whole-batch pipeline: L hops of (sample + relabel) in 3 L kernel
+// launches with no host round trip.
+//
+// Replaces the layer loops P2PCacheNodeClassificationSample{Uniform,Bias}
+// (src/sampling/sampler.cc:14-62) which, per hop, run ~15 launches (thrust lookup, 2 cub scans,
+// the sampling kernel, 2 torch::cat, 3 torch::full of the hash size, 4 thrust relabel passes,
+// 2 more scan kernels) and block twice on a D2H read (rowwise_sampling_p2p.cu:226-228,
+// tensor_relabel.cu:129).  At batch 1024 every one of those kernels is a few microseconds, so the
+// reference's hop is launch- and sync-bound; here a hop is three dependent kernels:
+//
+//   fused_pick  : warp per seed.  Location-table probe, indptr pair from the owner (local HBM /
+//                 NVLink peer / pinned host), selection (sampling_device.cuh), neighbours written
+//                 to a PADDED slot array (seed i owns slots [i k, (i+1) k)) - so no prefix sum is
+//                 needed before sampling - and every seed / neighbour id is inserted on the fly
+//                 into the hop's relabel table (CAS on the key, atomicMin on the item index =
+//                 first occurrence).  The same kernel also wipes the slots the previous hop
+//                 touched in the other table (two tables alternate), so no memset ever runs.
+//   fused_rank  : CTA per 64 seeds.  Flags first occurrences among the seeds (A) and among the
+//                 sampled neighbours (B), counts the edges (C), block scans; the last CTA to finish
+//                 turns the three per-tile totals into exclusive prefixes and publishes
+//                 nnz = C and |frontier| = A + B on the device.
+//   fused_emit  : thread per padded slot.  frontier[new id] = id for first occurrences, and the
+//                 COO is written compacted and relabelled: row = new id of the seed, col = new id
+//                 of the neighbour (new id = tile prefix + rank inside the tile).
+// The result is bit-identical to sample -> TensorRelabelCUDA({seeds, col}, {row, col}): `frontier`
+// is the first-occurrence-order unique of cat(seeds, coo_col), the COO is seed-major with the
+// neighbours of a seed in selection order (CSR order on the copy path).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "dgs_common.cuh"
+#include "p2p_server.h"
+#include "sampling_device.cuh"
+
+namespace dgsb {
+
+constexpr int kBkWarps = 8;
+constexpr int kBkThreads = 256;
+constexpr int kBkTile = 64;  // seeds per rank tile
+
+struct __align__(16) RlSlot {
+  long long key;       // -1 empty
+  unsigned int first;  // smallest item index holding this key
+  unsigned int lrank;  // rank of that first occurrence inside its tile
+};
+
+struct HopState {        // per-hop arrays that must survive until the next hop's cleanup
+  int *cnt;              // [S_max]   edges kept for seed i
+  unsigned int *pos_seed;  // [S_max]   table slot of seed i
+  unsigned int *pos_col;   // [E_max]   table slot of padded neighbour slot e
+  RlSlot *table;
+};
+
+struct BlocksWs {
+  unsigned int *done;
+  long long *pending_S;              // live seed count of the hop whose table is still dirty
+  long long *prefA, *prefB, *prefC;  // [tiles_max + 1]
+  int *loff;                         // [S_max] exclusive edge offset of seed i inside its tile
+  void *pad_col;                     // [E_max] ids
+  HopState hop[2];
+  int64_t cap;                       // slots per table
+};
+
+struct BlocksPlan {
+  int64_t S_max, E_max, tiles_max, cap, bytes;
+};
+
+static inline int64_t up256(int64_t x) { return (x + 255) / 256 * 256; }
+
+static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_out, BlocksPlan *p,
+                       char *base, BlocksWs *ws) {
+  DGS_REQUIRE(L >= 1 && L <= 16, "sample_blocks: 1..16 layers supported");
+  int64_t ub = num_seeds < 1 ? 1 : num_seeds, S_max = 1, E_max = 1, items_max = 1;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[L - 1 - l];
+    DGS_REQUIRE(k >= 0, "sample_blocks: fan_out must be >= 0 (use the per-hop entry for -1)");
+    const int64_t e = ub * k;
+    DGS_REQUIRE(ub + e < (1ll << 32) - 2, "sample_blocks: more than 2^32 items in one hop");
+    if (ub > S_max) S_max = ub;
+    if (e > E_max) E_max = e;
+    if (ub + e > items_max) items_max = ub + e;
+    ub += e;
+  }
+  int64_t cap = 64;
+  while (cap < 2 * items_max) cap <<= 1;
+  const int idb = itype == DGS_I64 ? 8 : 4;
+  p->S_max = S_max;
+  p->E_max = E_max;
+  p->tiles_max = (S_max + kBkTile - 1) / kBkTile;
+  p->cap = cap;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char *q = base ? base + off : nullptr;
+    off += up256(bytes);
+    return q;
+  };
+  char *done = take(256);
+  char *pa = take((p->tiles_max + 1) * 8), *pb = take((p->tiles_max + 1) * 8),
+       *pc = take((p->tiles_max + 1) * 8);
+  char *loff = take(S_max * 4);
+  char *pad = take(E_max * idb);
+  char *h[2][4];
+  for (int b = 0; b < 2; ++b) {
+    h[b][0] = take(S_max * 4);
+    h[b][1] = take(S_max * 4);
+    h[b][2] = take(E_max * 4);
+    h[b][3] = take(cap * (int64_t)sizeof(RlSlot));
+  }
+  p->bytes = off;
+  if (ws) {
+    ws->done = (unsigned int *)done;
+    ws->pending_S = (long long *)(done + 64);
+    ws->prefA = (long long *)pa;
+    ws->prefB = (long long *)pb;
+    ws->prefC = (long long *)pc;
+    ws->loff = (int *)loff;
+    ws->pad_col = pad;
+    for (int b = 0; b < 2; ++b) {
+      ws->hop[b].cnt = (int *)h[b][0];
+      ws->hop[b].pos_seed = (unsigned int *)h[b][1];
+      ws->hop[b].pos_col = (unsigned int *)h[b][2];
+      ws->hop[b].table = (RlSlot *)h[b][3];
+    }
+    ws->cap = cap;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ unsigned int rl_insert(RlSlot *table, uint64_t mask, long long key,
+                                                  unsigned int item) {
+  uint64_t pos = mix64((uint64_t)key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS((unsigned long long *)&table[pos].key,
+                                        (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)key) break;
+    pos = (pos + 1) & mask;
+  }
+  atomicMin(&table[pos].first, item);
+  return (unsigned int)pos;
+}
+
+// N independent inserts with all first-probe CAS operations in flight before any result is used
+// (a single rl_insert is a dependent CAS -> atomicMin chain of ~1 us).
+template <int N>
+__device__ __forceinline__ void rl_insert_batch(RlSlot *table, uint64_t mask, const long long (&key)[N],
+                                                const unsigned int (&item)[N], const bool (&ok)[N],
+                                                unsigned int (&out_pos)[N]) {
+  uint64_t pos[N];
+  unsigned long long prev[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    pos[u] = mix64((uint64_t)key[u]) & mask;
+    if (ok[u])
+      prev[u] = atomicCAS((unsigned long long *)&table[pos[u]].key, (unsigned long long)kEmptyKey,
+                          (unsigned long long)key[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    if (!ok[u]) continue;
+    while (prev[u] != (unsigned long long)kEmptyKey && prev[u] != (unsigned long long)key[u]) {
+      pos[u] = (pos[u] + 1) & mask;
+      prev[u] = atomicCAS((unsigned long long *)&table[pos[u]].key, (unsigned long long)kEmptyKey,
+                          (unsigned long long)key[u]);
+    }
+    atomicMin(&table[pos[u]].first, item[u]);
+    out_pos[u] = (unsigned int)pos[u];
+  }
+}
+
+__device__ __forceinline__ void rl_wipe(RlSlot *table, unsigned int pos) {
+  *reinterpret_cast<int4 *>(&table[pos]) = make_int4(-1, -1, -1, -1);
+}
+
+// wipe every slot the given hop touched (idempotent; duplicates wipe the same slot twice)
+__device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < S; i += stride) rl_wipe(h.table, h.pos_seed[i]);
+  if (k > 0) {
+    const int64_t E = S * k;
+    for (int64_t e = tid; e < E; e += stride) {
+      const int64_t i = e / k;
+      const int j = (int)(e - i * k);
+      if (j < h.cnt[i]) rl_wipe(h.table, h.pos_col[e]);
+    }
+  }
+}
+
+template <typename IdT>
+struct PadEmit {
+  IdT *pcol;
+  unsigned int *ppos;
+  RlSlot *table;
+  uint64_t mask;
+  unsigned int item_base;
+  __device__ __forceinline__ void operator()(int j, IdT v) {
+    pcol[j] = v;
+    ppos[j] = rl_insert(table, mask, (long long)v, item_base + (unsigned int)j);
+  }
+};
+
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads)
+fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
+                  const int64_t *__restrict__ S_dev, int k, uint64_t rng_key, IdT *pad_col,
+                  HopState cur, uint64_t cap_mask, HopState prev, int64_t prev_S_ub,
+                  const long long *__restrict__ prev_S_dev, int prev_k, int gmem_scratch) {
+  extern __shared__ __align__(16) unsigned char pick_smem[];
+  // (1) wipe the other table: the slots the previous hop touched
+  if (prev.table != nullptr) {
+    const int64_t pS = min((int64_t)*prev_S_dev, prev_S_ub);
+    wipe_hop(prev, pS, prev_k);
+  }
+  // (2) sample this hop
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  const int64_t warps_total = (int64_t)gridDim.x * kBkWarps;
+  int *w_idx = nullptr;
+  float *w_key = nullptr;
+  if (k > 0 && !gmem_scratch) {
+    if (MODE == kUniform) {
+      w_idx = reinterpret_cast<int *>(pick_smem) + (size_t)warp * k;
+    } else if (MODE == kBias) {
+      w_key = reinterpret_cast<float *>(pick_smem) + (size_t)warp * 2 * k;
+      w_idx = reinterpret_cast<int *>(w_key + k);
+    }
+  }
+  for (int64_t i = (int64_t)blockIdx.x * kBkWarps + warp; i < S; i += warps_total) {
+    const long long nid = (long long)seeds[i];
+    int dev;
+    long long begin, deg64;
+    resolve_seed<ET>(g, nid, &dev, &begin, &deg64);
+    const int deg = (int)deg64;
+    const bool with_replace = (MODE == kUniformReplace || MODE == kBiasReplace);
+    const bool copy_path = !with_replace && deg <= k;
+    const int cnt = deg == 0 ? 0 : (copy_path ? deg : k);
+    if (lane == 0) {
+      cur.cnt[i] = cnt;
+      cur.pos_seed[i] = rl_insert(cur.table, cap_mask, nid, (unsigned int)i);
+    }
+    if (cnt == 0) continue;
+    const IdT *row =
+        reinterpret_cast<const IdT *>(dev < 0 ? g.indices : g.sh_indices.p[dev]) + begin;
+    const float *wrow = nullptr;
+    if (MODE == kBias || MODE == kBiasReplace)
+      wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
+    PadEmit<IdT> emit{pad_col + i * k, cur.pos_col + i * k, cur.table, cap_mask,
+                      (unsigned int)(S_ub + i * k)};
+    if (gmem_scratch && !copy_path) {
+      w_idx = reinterpret_cast<int *>(emit.pcol);
+      w_key = reinterpret_cast<float *>(emit.ppos);
+    }
+    warp_select<IdT, MODE, PadEmit<IdT>>(row, wrow, deg, k, copy_path, rng_key, (uint64_t)i, lane,
+                                        w_idx, w_key, emit);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Tile version of fused_pick (num_picks small enough for shared memory): a CTA owns 128 seeds.
+//   A  thread per seed : probe, indptr pair, count, insert the seed id        (128 chains in flight)
+//   B1 warp per seed   : selection -> POSITIONS inside the row, kept in shared memory (no loads
+//                        for uniform sampling; the weight scan for biased sampling)
+//   B2 thread per slot : neighbour load, padded store, table insert           (every slot of the
+//                        tile is an independent load -> CAS -> atomicMin chain)
+// The warp-per-seed kernel above serialises these chains per seed; here the memory-level
+// parallelism is the tile's whole edge set.  Same RNG counters => identical samples.
+constexpr int kPkSeeds = 128;
+
+template <typename IdT>
+struct PosEmit {
+  unsigned int *p;
+  __device__ __forceinline__ void operator()(int j, IdT v) { p[j] = (unsigned int)v; }
+};
+
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads)
+fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
+                       const int64_t *__restrict__ S_dev, int k, uint64_t rng_key,
+                       IdT *__restrict__ pad_col, HopState cur, uint64_t cap_mask, HopState prev,
+                       int64_t prev_S_ub, const long long *__restrict__ prev_S_dev, int prev_k) {
+  extern __shared__ __align__(16) unsigned char pick_smem[];
+  __shared__ const IdT *s_row[kPkSeeds];
+  __shared__ const float *s_w[kPkSeeds];
+  __shared__ int s_deg[kPkSeeds];
+  __shared__ int s_cnt[kPkSeeds];
+  unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
+  float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
+  if (prev.table != nullptr) {
+    const int64_t pS = min((int64_t)*prev_S_dev, prev_S_ub);
+    wipe_hop(prev, pS, prev_k);
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  const int64_t tiles = (S + kPkSeeds - 1) / kPkSeeds;
+  const bool with_replace = (MODE == kUniformReplace || MODE == kBiasReplace);
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t i0 = tile * kPkSeeds;
+    const int ns = (int)min((int64_t)kPkSeeds, S - i0);
+    __syncthreads();  // previous tile's readers are done with the shared arrays
+    if (tid < ns) {
+      const int64_t i = i0 + tid;
+      const long long nid = (long long)seeds[i];
+      int dev;
+      long long begin, deg64;
+      resolve_seed<ET>(g, nid, &dev, &begin, &deg64);
+      const int deg = (int)deg64;
+      const int cnt = deg == 0 ? 0 : ((!with_replace && deg <= k) ? deg : k);
+      s_row[tid] = reinterpret_cast<const IdT *>(dev < 0 ? g.indices : g.sh_indices.p[dev]) + begin;
+      if (MODE == kBias || MODE == kBiasReplace)
+        s_w[tid] = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
+      s_deg[tid] = deg;
+      s_cnt[tid] = cnt;
+      cur.cnt[i] = cnt;
+      cur.pos_seed[i] = rl_insert(cur.table, cap_mask, nid, (unsigned int)i);
+    }
+    __syncthreads();
+    // B1: positions of the sampled rows
+    if (MODE == kUniform) {
+      // Floyd's subset sampling, one THREAD per seed (k draws, O(k^2) compares against the
+      // positions already in shared memory): the whole tile is selected in one short burst
+      if (tid < ns) {
+        const int deg = s_deg[tid];
+        if (deg > k) {
+          unsigned int *P = s_pick + (size_t)tid * k;
+          uint4 r4 = make_uint4(0, 0, 0, 0);
+          for (int t = 0; t < k; ++t) {
+            if ((t & 3) == 0) r4 = Philox::gen(rng_key, (uint64_t)(i0 + tid), (uint64_t)(t >> 2));
+            const uint32_t rr = (t & 3) == 0 ? r4.x : ((t & 3) == 1 ? r4.y : ((t & 3) == 2 ? r4.z : r4.w));
+            const unsigned int J = (unsigned int)(deg - k + t);
+            const unsigned int r = rand_below(rr, J + 1);
+            bool dup = false;
+            for (int q = 0; q < t; ++q) dup |= (P[q] == r);
+            P[t] = dup ? J : r;
+          }
+        }
+      }
+    } else if (MODE != kUniformReplace) {
+      for (int s_ = warp; s_ < ns; s_ += kBkWarps) {
+        const int deg = s_deg[s_];
+        if (deg == 0 || (!with_replace && deg <= k)) continue;  // copy path: position j
+        PosEmit<IdT> pe{s_pick + (size_t)s_ * k};
+        warp_select<IdT, MODE, PosEmit<IdT>, true>(nullptr, s_w[s_], deg, k, false, rng_key,
+                                                   (uint64_t)(i0 + s_), lane,
+                                                   reinterpret_cast<int *>(pe.p),
+                                                   s_key + (size_t)warp * k, pe);
+      }
+    }
+    __syncthreads();
+    // B2: one slot per thread; 4 independent row loads, then 4 independent table inserts in flight
+    const int slots = ns * k;
+    for (int base = tid; base < slots; base += kBkThreads * 4) {
+      long long v[4];
+      unsigned int item[4], pos[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int el = base + u * kBkThreads;
+        ok[u] = false;
+        v[u] = 0;
+        item[u] = (unsigned int)(S_ub + i0 * k + el);
+        if (el < slots) {
+          const int si = el / k;
+          const int j = el - si * k;
+          if (j < s_cnt[si]) {
+            const int deg = s_deg[si];
+            unsigned int p;
+            if (MODE == kUniformReplace)
+              p = rand_below(philox_u32(rng_key, (uint64_t)(i0 + si), (uint32_t)j), (uint32_t)deg);
+            else
+              p = (!with_replace && deg <= k) ? (unsigned int)j : s_pick[el];
+            v[u] = (long long)s_row[si][p];
+            ok[u] = true;
+          }
+        }
+      }
+      rl_insert_batch<4>(cur.table, cap_mask, v, item, ok, pos);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ok[u]) {
+          const int64_t e = i0 * k + (base + u * kBkThreads);
+          pad_col[e] = (IdT)v[u];
+          cur.pos_col[e] = pos[u];
+        }
+      }
+    }
+  }
+}
+
+constexpr int kRkItems = 8;  // padded slots per thread and pass (blocked arrangement)
+
+__global__ void __launch_bounds__(kBkThreads)
+fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopState cur,
+                  BlocksWs ws, int64_t *__restrict__ out_nnz, int64_t *__restrict__ out_nfront) {
+  __shared__ long long s_scan[32];
+  __shared__ long long s_total;
+  __shared__ int s_cnt[kBkTile];
+  __shared__ bool s_last;
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  const int tid = threadIdx.x;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t i0 = tile * kBkTile;
+    const int ns = (int)min((int64_t)kBkTile, S - i0);
+    __syncthreads();
+    // A: first occurrences among the tile's seeds, C: its edge count - one packed scan
+    long long fa = 0, c = 0;
+    unsigned int slot_a = 0;
+    if (tid < ns) {
+      slot_a = cur.pos_seed[i0 + tid];
+      c = cur.cnt[i0 + tid];
+      s_cnt[tid] = (int)c;
+      fa = (cur.table[slot_a].first == (unsigned int)(i0 + tid)) ? 1 : 0;
+    }
+    const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
+    const long long totA = s_total >> 32, totC = s_total & 0xffffffffll;
+    if (fa) cur.table[slot_a].lrank = (unsigned int)(rac >> 32);
+    if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
+    // B: first occurrences among the tile's sampled neighbours.  The tile's padded slots are
+    // contiguous (e = i0 k + el); every thread owns kRkItems consecutive slots, issues all its
+    // table probes first, then one block scan ranks the whole pass.
+    long long carry = 0;
+    const int items = ns * k;
+    const int64_t e0 = i0 * k;
+    for (int base = 0; base < items; base += kBkThreads * kRkItems) {
+      const int el0 = base + tid * kRkItems;
+      unsigned int slot[kRkItems];
+      bool valid[kRkItems];
+#pragma unroll
+      for (int u = 0; u < kRkItems; ++u) {
+        const int el = el0 + u;
+        valid[u] = false;
+        if (el < items) {
+          const int si = el / k;
+          valid[u] = (el - si * k) < s_cnt[si];
+          if (valid[u]) slot[u] = cur.pos_col[e0 + el];
+        }
+      }
+      unsigned int first[kRkItems];
+#pragma unroll
+      for (int u = 0; u < kRkItems; ++u)
+        if (valid[u]) first[u] = cur.table[slot[u]].first;
+      int mine = 0;
+      bool fb[kRkItems];
+#pragma unroll
+      for (int u = 0; u < kRkItems; ++u) {
+        fb[u] = valid[u] && first[u] == (unsigned int)(S_ub + e0 + el0 + u);
+        mine += fb[u] ? 1 : 0;
+      }
+      long long r = carry + block_exclusive_scan<long long>((long long)mine, s_scan, &s_total);
+#pragma unroll
+      for (int u = 0; u < kRkItems; ++u)
+        if (fb[u]) cur.table[slot[u]].lrank = (unsigned int)(r++);
+      carry += s_total;
+    }
+    if (tid == 0) {
+      ws.prefA[tile] = totA;
+      ws.prefB[tile] = carry;
+      ws.prefC[tile] = totC;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int t = atomicAdd(ws.done, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    // exclusive scans of the three per-tile totals: every thread owns a run of consecutive tiles
+    __threadfence();
+    volatile long long *pa = ws.prefA, *pb = ws.prefB, *pc = ws.prefC;
+    const int64_t per = (tiles + kBkThreads - 1) / kBkThreads;
+    const int64_t t0 = (int64_t)tid * per, t1 = min(tiles, t0 + per);
+    long long sa = 0, sb = 0, sc = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+      sa += pa[t];
+      sb += pb[t];
+      sc += pc[t];
+    }
+    long long xa = block_exclusive_scan<long long>(sa, s_scan, &s_total);
+    const long long totA = s_total;
+    long long xb = block_exclusive_scan<long long>(sb, s_scan, &s_total);
+    const long long totB = s_total;
+    long long xc = block_exclusive_scan<long long>(sc, s_scan, &s_total);
+    const long long totC = s_total;
+    for (int64_t t = t0; t < t1; ++t) {
+      const long long va = pa[t], vb = pb[t], vc = pc[t];
+      pa[t] = xa; pb[t] = xb; pc[t] = xc;
+      xa += va; xb += vb; xc += vc;
+    }
+    if (tid == 0) {
+      pa[tiles] = totA;
+      pb[tiles] = totB;
+      pc[tiles] = totC;
+      *out_nnz = totC;
+      *out_nfront = totA + totB;
+      *ws.done = 0;
+    }
+  }
+}
+
+// new id of the key stored in `s` (first occurrence f, rank inside its tile)
+__device__ __forceinline__ long long new_id(const RlSlot &s, int64_t S_ub, int k, long long totA,
+                                            const long long *__restrict__ prefA,
+                                            const long long *__restrict__ prefB) {
+  const unsigned int f = s.first;
+  if ((int64_t)f < S_ub) return prefA[f / kBkTile] + (long long)s.lrank;
+  const int64_t e = (int64_t)f - S_ub;
+  return totA + prefB[(e / k) / kBkTile] + (long long)s.lrank;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kBkThreads)
+fused_emit_kernel(const IdT *__restrict__ seeds, int64_t S_ub, const int64_t *__restrict__ S_dev,
+                  int k, const IdT *__restrict__ pad_col, HopState cur, BlocksWs ws,
+                  IdT *__restrict__ frontier, IdT *__restrict__ out_row, IdT *__restrict__ out_col) {
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  const long long totA = ws.prefA[tiles];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) *ws.pending_S = S;  // this hop's table is dirty until the next pick kernel wipes it
+  for (int64_t i = tid; i < S; i += stride) {
+    const RlSlot s = cur.table[cur.pos_seed[i]];
+    if (s.first == (unsigned int)i) frontier[ws.prefA[i / kBkTile] + (long long)s.lrank] = seeds[i];
+  }
+  if (k <= 0) return;
+  const int64_t E = S * k;
+  for (int64_t e = tid; e < E; e += stride) {
+    const int64_t i = e / k;
+    const int j = (int)(e - i * k);
+    if (j >= cur.cnt[i]) continue;
+    const RlSlot sc = cur.table[cur.pos_col[e]];
+    const long long cid = new_id(sc, S_ub, k, totA, ws.prefA, ws.prefB);
+    if ((int64_t)sc.first == S_ub + e) frontier[cid] = pad_col[e];
+    const RlSlot ss = cur.table[cur.pos_seed[i]];
+    const long long rid = ws.prefA[ss.first / kBkTile] + (long long)ss.lrank;
+    const long long o = ws.prefC[i / kBkTile] + (long long)ws.loff[i] + j;
+    out_row[o] = (IdT)rid;
+    out_col[o] = (IdT)cid;
+  }
+}
+
+__global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = make_int4(-1, -1, -1, -1);
+}
+
+int build_graph_src(const dgs_graph_t *g, GraphSrc *out);  // sampling.cu
+
+template <typename IdT, typename ET>
+static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seeds, int L,
+                         const int64_t *fan_out, int replace, uint64_t rng_seed, int64_t epoch,
+                         void *const *out_frontier, void *const *out_row, void *const *out_col,
+                         const int64_t *cap_edges, const int64_t *cap_frontier,
+                         int64_t *counts_dev, const BlocksWs &ws, cudaStream_t st) {
+  const bool bias = src.probs != nullptr || src.sh_probs.p[0] != nullptr;
+  const int mode = bias ? (replace ? kBiasReplace : kBias) : (replace ? kUniformReplace : kUniform);
+  const uint64_t cap_mask = (uint64_t)ws.cap - 1;
+  // upper bounds of every hop (the previous call on this workspace had the same ones)
+  int64_t ubs[16];
+  {
+    int64_t ub = num_seeds;
+    for (int l = 0; l < L; ++l) {
+      ubs[l] = ub;
+      ub += ub * fan_out[L - 1 - l];
+    }
+  }
+  // DGS_BLOCKS_TIMING=1: CUDA events after every kernel, printed (and synchronised!) per call
+  static const bool timing = getenv("DGS_BLOCKS_TIMING") != nullptr;
+  cudaEvent_t evs[3 * 16 + 1];
+  int nev = 0;
+  auto mark = [&]() {
+    if (timing) {
+      cudaEventCreate(&evs[nev]);
+      cudaEventRecord(evs[nev], st);
+      ++nev;
+    }
+  };
+  mark();
+  const IdT *cur_seeds = seeds;
+  const int64_t *cur_dev = nullptr;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k64 = fan_out[L - 1 - l];  // walked from the back (sampler.cc:20)
+    const int k = (int)k64;
+    const int64_t cur_ub = ubs[l];
+    const int64_t nnz_ub = cur_ub * k64;
+    DGS_REQUIRE(cap_edges[l] >= nnz_ub, "sample_blocks: layer %d edge capacity %lld < %lld", l,
+                (long long)cap_edges[l], (long long)nnz_ub);
+    DGS_REQUIRE(cap_frontier[l] >= cur_ub + nnz_ub,
+                "sample_blocks: layer %d frontier capacity %lld < %lld", l,
+                (long long)cap_frontier[l], (long long)(cur_ub + nnz_ub));
+    // Hops are numbered h = epoch L + l over the life of the workspace; hop h uses state h & 1 and
+    // wipes what hop h - 1 left in the other one (for l = 0 that is the last hop of the previous
+    // call, whose live seed count the emit kernel parked in ws.pending_S; 0 after ws_init).
+    const int64_t h = epoch * L + l;
+    const HopState &cur = ws.hop[h & 1];
+    const HopState &prev = ws.hop[(h + 1) & 1];
+    const int pl = l > 0 ? l - 1 : L - 1;
+    const int64_t prev_ub = ubs[pl];
+    const int prev_k = (int)fan_out[L - 1 - pl];
+    const long long *prev_dev = ws.pending_S;
+    int64_t *nnz_dev = counts_dev + 2 * l, *nf_dev = counts_dev + 2 * l + 1;
+    const uint64_t key = rng_seed + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
+    // shared memory: tile kernel = 128 k positions (+ 8 k keys when biased)
+    size_t smem_tile = (size_t)kPkSeeds * k * sizeof(int);
+    if (mode == kBias) smem_tile += (size_t)kBkWarps * k * sizeof(float);
+    if (k > 0 && smem_tile <= 64 * 1024) {
+      const int grid = std::max(grid_for(cur_ub, kPkSeeds, 4),
+                                grid_for(prev_ub * (1 + (int64_t)prev_k), kBkThreads * 4, 4));
+#define DGS_TPICK(M)                                                                            \
+  do {                                                                                          \
+    auto kern = fused_pick_tile_kernel<IdT, ET, M>;                                             \
+    if (smem_tile > 48 * 1024)                                                                  \
+      DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       (int)smem_tile));                                        \
+    kern<<<grid, kBkThreads, smem_tile, st>>>(src, cur_seeds, cur_ub, cur_dev, k, key,          \
+                                              (IdT *)ws.pad_col, cur, cap_mask, prev, prev_ub,  \
+                                              prev_dev, prev_k);                                \
+  } while (0)
+      switch (mode) {
+        case kUniform: DGS_TPICK(kUniform); break;
+        case kUniformReplace: DGS_TPICK(kUniformReplace); break;
+        case kBias: DGS_TPICK(kBias); break;
+        default: DGS_TPICK(kBiasReplace); break;
+      }
+#undef DGS_TPICK
+    } else {
+      size_t smem = 0;
+      if (k > 32 && mode == kUniform) smem = (size_t)kBkWarps * k * sizeof(int);
+      if (k > 0 && mode == kBias) smem = (size_t)kBkWarps * k * 2 * sizeof(float);
+      int gmem_scratch = 0;
+      if (smem > 96 * 1024) {
+        smem = 0;
+        gmem_scratch = 1;
+      }
+      const int grid_pick = std::max(grid_for(cur_ub, kBkWarps, 8),
+                                     grid_for(prev_ub * (1 + (int64_t)prev_k), kBkThreads * 4, 8));
+#define DGS_FPICK(M)                                                                            \
+  do {                                                                                          \
+    auto kern = fused_pick_kernel<IdT, ET, M>;                                                  \
+    if (smem > 48 * 1024)                                                                       \
+      DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       (int)smem));                                             \
+    kern<<<grid_pick, kBkThreads, smem, st>>>(src, cur_seeds, cur_ub, cur_dev, k, key,          \
+                                              (IdT *)ws.pad_col, cur, cap_mask, prev, prev_ub,  \
+                                              prev_dev, prev_k, gmem_scratch);                  \
+  } while (0)
+      switch (mode) {
+        case kUniform: DGS_FPICK(kUniform); break;
+        case kUniformReplace: DGS_FPICK(kUniformReplace); break;
+        case kBias: DGS_FPICK(kBias); break;
+        default: DGS_FPICK(kBiasReplace); break;
+      }
+#undef DGS_FPICK
+    }
+    DGS_LAUNCH_CHECK();
+    mark();
+    const int grid_rank = grid_for(cur_ub, kBkTile, 8);
+    fused_rank_kernel<<<grid_rank, kBkThreads, 0, st>>>(cur_ub, cur_dev, k, cur, ws, nnz_dev, nf_dev);
+    DGS_LAUNCH_CHECK();
+    mark();
+    const int grid_emit = grid_for(cur_ub + nnz_ub, kBkThreads, 8);
+    fused_emit_kernel<IdT><<<grid_emit, kBkThreads, 0, st>>>(
+        cur_seeds, cur_ub, cur_dev, k, (const IdT *)ws.pad_col, cur, ws, (IdT *)out_frontier[l],
+        (IdT *)out_row[l], (IdT *)out_col[l]);
+    DGS_LAUNCH_CHECK();
+    mark();
+    cur_seeds = (const IdT *)out_frontier[l];
+    cur_dev = nf_dev;
+  }
+  if (timing) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[dgs blocks timing us]");
+    for (int i = 1; i < nev; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+      fprintf(stderr, " %s%.1f", (i - 1) % 3 == 0 ? "| " : "", ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(evs[i]);
+  }
+  return 0;
+}
+
+}  // namespace dgsb
+
+using namespace dgsb;
+
+extern "C" int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
+                                              const int64_t *fan_out) {
+  BlocksPlan p;
+  if (!fan_out || blocks_plan(itype, num_seeds, num_layers, fan_out, &p, nullptr, nullptr)) return -1;
+  return p.bytes;
+}
+
+extern "C" int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
+                                         int num_layers, const int64_t *fan_out, void *stream) {
+  DGS_REQUIRE(ws && fan_out, "dgs_sample_blocks_ws_init: null argument");
+  BlocksPlan p;
+  BlocksWs w;
+  if (blocks_plan(itype, num_seeds, num_layers, fan_out, &p, (char *)ws, &w)) return 1;
+  DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks_ws_init: workspace %lld < %lld bytes",
+              (long long)ws_bytes, (long long)p.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  DGS_CUDA_OK(cudaMemsetAsync(w.done, 0, 256, st));
+  for (int b = 0; b < 2; ++b) {
+    blocks_ws_init_kernel<<<grid_for(p.cap, 256, 8), 256, 0, st>>>((int4 *)w.hop[b].table, p.cap);
+    DGS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                                 int num_layers, const int64_t *fan_out, int replace,
+                                 uint64_t rng_seed, void *const *out_frontier,
+                                 void *const *out_row, void *const *out_col,
+                                 const int64_t *cap_edges, const int64_t *cap_frontier,
+                                 int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
+                                 void *stream) {
+  DGS_REQUIRE(g && fan_out && out_frontier && out_row && out_col && cap_edges && cap_frontier &&
+                  counts_dev && ws,
+              "dgs_sample_blocks: null argument");
+  DGS_REQUIRE(num_seeds >= 0 && epoch >= 0, "dgs_sample_blocks: negative seed count / epoch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_seeds == 0) {
+    DGS_REQUIRE(num_layers >= 1 && num_layers <= 16, "dgs_sample_blocks: 1..16 layers supported");
+    DGS_CUDA_OK(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 2 * num_layers, st));
+    return 0;
+  }
+  DGS_REQUIRE(seeds != nullptr, "dgs_sample_blocks: null seeds");
+  BlocksPlan p;
+  BlocksWs w;
+  if (blocks_plan(g->itype, num_seeds, num_layers, fan_out, &p, (char *)ws, &w)) return 1;
+  DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks: workspace %lld < %lld bytes",
+              (long long)ws_bytes, (long long)p.bytes);
+  GraphSrc src;
+  if (build_graph_src(g, &src)) return 1;
+  DGS_ITYPE_SWITCH(g->itype, IdT, {
+    DGS_ITYPE_SWITCH(g->etype, ET, {
+      return launch_blocks<IdT, ET>(src, (const IdT *)seeds, num_seeds, num_layers, fan_out,
+                                    replace, rng_seed, epoch, out_frontier, out_row, out_col,
+                                    cap_edges, cap_frontier, counts_dev, w, st);
+    });
+  });
+  return 0;
+}

@@ -30,20 +30,12 @@
 // counter (seed index, draw index): results do not depend on grid or block shape.
 #include "dgs_common.cuh"
 #include "p2p_server.h"
+#include "sampling_device.cuh"
 
 namespace dgsb {
 
 constexpr int kPlanThreads = 256;  // = seeds per plan tile
 constexpr int kPickWarps = 8;
-
-struct GraphSrc {
-  const void *indptr;
-  const void *indices;
-  const float *probs;
-  PtrTable sh_indptr, sh_indices, sh_probs;
-  const LocSlot *loc;
-  uint64_t cap_mask;
-};
 
 struct SampleWs {
   long long *begin;       // [M] first edge of the seed's row inside its source array
@@ -81,16 +73,6 @@ static int64_t ws_layout(int64_t M, char *base, SampleWs *ws) {
   return off;
 }
 
-template <typename T>
-__device__ __forceinline__ T warp_inclusive_scan(T v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    T t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
-
 // ------------------------------------------------------------------------------------------
 template <typename IdT, typename ET>
 __global__ void __launch_bounds__(kPlanThreads)
@@ -107,22 +89,9 @@ plan_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
     long long cnt = 0;
     if (i < S) {
       const long long nid = (long long)seeds[i];
-      long long begin, end;
-      int dev = -1;
-      long long v = -1;
-      if (g.loc != nullptr) v = loc_lookup(g.loc, g.cap_mask, nid);
-      if (v >= 0) {
-        dev = (int)((v >> kDevShift) & 0xff);
-        const long long idx = v & kIdxMask;
-        const ET *ip = reinterpret_cast<const ET *>(g.sh_indptr.p[dev]);
-        begin = (long long)ip[idx];
-        end = (long long)ip[idx + 1];
-      } else {
-        const ET *ip = reinterpret_cast<const ET *>(g.indptr);
-        begin = (long long)ip[nid];
-        end = (long long)ip[nid + 1];
-      }
-      const long long deg = end - begin;
+      long long begin, deg;
+      int dev;
+      resolve_seed<ET>(g, nid, &dev, &begin, &deg);
       if (replace)
         cnt = (deg == 0 || k < 0) ? (k < 0 ? deg : 0) : k;
       else
@@ -165,32 +134,15 @@ plan_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
 }
 
 // ------------------------------------------------------------------------------------------
-enum PickMode { kUniform = 0, kUniformReplace = 1, kBias = 2, kBiasReplace = 3 };
-
-__device__ __forceinline__ uint32_t philox_u32(uint64_t key, uint64_t item, uint32_t draw) {
-  uint4 r = Philox::gen(key, item, (uint64_t)(draw >> 2));
-  const uint32_t c = draw & 3u;
-  return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
-}
-
-// Write the k picked neighbours.  w_idx may alias the first 4 k bytes of ocol (global scratch
-// mode): chunks are processed from the top and every lane reads its position before any lane
-// writes, so an 8-byte ocol[j] only overwrites positions >= j that were already consumed.
 template <typename IdT>
-__device__ __forceinline__ void emit_picks(const IdT *__restrict__ row, const int *w_idx, int k,
-                                           int lane, IdT seed, IdT *orow, IdT *ocol) {
-  for (int j0 = ((k - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
-    const int j = j0 + lane;
-    int p = 0;
-    if (j < k) p = w_idx[j];
-    __syncwarp();
-    if (j < k) {
-      ocol[j] = row[p];
-      orow[j] = seed;
-    }
-    __syncwarp();
+struct CooEmit {
+  IdT *orow, *ocol;
+  IdT seed;
+  __device__ __forceinline__ void operator()(int j, IdT v) {
+    ocol[j] = v;
+    orow[j] = seed;
   }
-}
+};
 
 template <typename IdT, typename ET, int MODE>
 __global__ void __launch_bounds__(kPickWarps * 32)
@@ -238,167 +190,12 @@ pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t num_seeds,
       w_idx = reinterpret_cast<int *>(ocol);
     }
 
-    if (copy_path) {
-      // CSR-order copy, 4 independent loads in flight per lane
-      int j = lane;
-      for (; j + 96 < deg; j += 128) {
-        IdT a = row[j], b = row[j + 32], c = row[j + 64], d = row[j + 96];
-        ocol[j] = a; ocol[j + 32] = b; ocol[j + 64] = c; ocol[j + 96] = d;
-        orow[j] = seed; orow[j + 32] = seed; orow[j + 64] = seed; orow[j + 96] = seed;
-      }
-      for (; j < deg; j += 32) {
-        ocol[j] = row[j];
-        orow[j] = seed;
-      }
-      continue;
-    }
-
-    if (MODE == kUniformReplace) {
-      for (int j = lane; j < k; j += 32) {
-        uint32_t p = rand_below(philox_u32(rng_key, (uint64_t)i, (uint32_t)j), (uint32_t)deg);
-        ocol[j] = row[p];
-        orow[j] = seed;
-      }
-    } else if (MODE == kUniform) {
-      // Floyd: for t = 0..k-1, J = deg-k+t: r = U[0, J]; pick (r already chosen ? J : r)
-      if (k <= 32) {
-        uint32_t r_mine = 0;
-        if (lane < k)
-          r_mine = rand_below(philox_u32(rng_key, (uint64_t)i, (uint32_t)lane),
-                              (uint32_t)(deg - k + lane + 1));
-        uint32_t mine = 0xffffffffu;  // lane t holds the t-th pick
-        for (int t = 0; t < k; ++t) {
-          const uint32_t r = __shfl_sync(0xffffffffu, r_mine, t);
-          const bool dup = __any_sync(0xffffffffu, lane < t && mine == r);
-          if (lane == t) mine = dup ? (uint32_t)(deg - k + t) : r;
-        }
-        if (lane < k) {
-          ocol[lane] = row[mine];
-          orow[lane] = seed;
-        }
-      } else {
-        for (int t0 = 0; t0 < k; t0 += 32) {
-          const int t_mine = t0 + lane;
-          uint32_t r_mine = 0;
-          if (t_mine < k)
-            r_mine = rand_below(philox_u32(rng_key, (uint64_t)i, (uint32_t)t_mine),
-                                (uint32_t)(deg - k + t_mine + 1));
-          const int lim = min(32, k - t0);
-          for (int tt = 0; tt < lim; ++tt) {
-            const int t = t0 + tt;
-            const uint32_t r = __shfl_sync(0xffffffffu, r_mine, tt);
-            bool found = false;
-            for (int c = lane; c < t; c += 32) found |= ((uint32_t)w_idx[c] == r);
-            const bool dup = __any_sync(0xffffffffu, found);
-            if (lane == 0) w_idx[t] = dup ? (deg - k + t) : (int)r;
-            __syncwarp();
-          }
-        }
-        emit_picks(row, w_idx, k, lane, seed, orow, ocol);
-      }
-    } else if (MODE == kBias) {
-      const float *wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
-      // fill the reservoir with the first k items
-      for (int t = lane; t < k; t += 32) {
-        const float w = wrow[t];
-        const float u = u32_to_unit(philox_u32(rng_key, (uint64_t)i, (uint32_t)t));
-        w_key[t] = w > 0.f ? __log2f(u) / w : -INFINITY;
-        w_idx[t] = t;
-      }
-      __syncwarp();
-      // (min key, its slot) over the reservoir
-      float lmin = INFINITY;
-      int lslot = -1;
-      for (int c = lane; c < k; c += 32) {
-        const float v = w_key[c];
-        if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
-      }
-      float wmin = lmin;
-      int wslot = lslot;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-        const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-        if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
-      }
-      for (int t0 = k; t0 < deg; t0 += 32) {
-        const int t = t0 + lane;
-        float key = -INFINITY;
-        if (t < deg) {
-          const float w = wrow[t];
-          const float u = u32_to_unit(philox_u32(rng_key, (uint64_t)i, (uint32_t)t));
-          key = w > 0.f ? __log2f(u) / w : -INFINITY;
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float ck = __shfl_sync(0xffffffffu, key, src);
-          const int ci = t0 + src;
-          if (ck > wmin) {  // warp-uniform
-            if (lane == 0) { w_key[wslot] = ck; w_idx[wslot] = ci; }
-            __syncwarp();
-            lmin = INFINITY;
-            lslot = -1;
-            for (int c = lane; c < k; c += 32) {
-              const float v = w_key[c];
-              if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
-            }
-            wmin = lmin;
-            wslot = lslot;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-              const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-              if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
-            }
-          }
-        }
-      }
-      __syncwarp();
-      emit_picks(row, w_idx, k, lane, seed, orow, ocol);
-    } else {  // kBiasReplace
-      const float *wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
-      // pass 1: total weight, with exactly the arithmetic of pass 2
-      float total = 0.f;
-      for (int c = 0; c < deg; c += 32) {
-        float w = (c + lane < deg) ? fmaxf(wrow[c + lane], 0.f) : 0.f;
-        float inc = warp_inclusive_scan<float>(w, lane);
-        total = total + __shfl_sync(0xffffffffu, inc, 31);
-      }
-      for (int j0 = 0; j0 < k; j0 += 32) {
-        const int j = j0 + lane;
-        const bool live = j < k;
-        float thr = 0.f;
-        if (live) thr = u32_to_unit(philox_u32(rng_key, (uint64_t)i, (uint32_t)j)) * total;
-        int mypos = deg - 1;  // u == 1 / rounding: clamp like MIN(item, deg - 1), :212
-        bool done = !live;
-        float running = 0.f;
-        for (int c = 0; c < deg; c += 32) {
-          float w = (c + lane < deg) ? fmaxf(wrow[c + lane], 0.f) : 0.f;
-          float inc = warp_inclusive_scan<float>(w, lane);
-          const float cdf = running + inc;
-          const float chunk_end = running + __shfl_sync(0xffffffffu, inc, 31);
-          unsigned mask = __ballot_sync(0xffffffffu, !done && thr < chunk_end);
-          while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float r = __shfl_sync(0xffffffffu, thr, src);
-            const unsigned b = __ballot_sync(0xffffffffu, cdf > r);
-            if (lane == src) {
-              mypos = c + __ffs(b) - 1;
-              done = true;
-            }
-          }
-          running = chunk_end;
-          if (__all_sync(0xffffffffu, done)) break;
-        }
-        if (live) {
-          ocol[j] = row[mypos];
-          orow[j] = seed;
-        }
-      }
-    }
+    const float *wrow = nullptr;
+    if (MODE == kBias || MODE == kBiasReplace)
+      wrow = (dev < 0 ? g.probs : reinterpret_cast<const float *>(g.sh_probs.p[dev])) + begin;
+    CooEmit<IdT> emit{orow, ocol, seed};
+    warp_select<IdT, MODE, CooEmit<IdT>>(row, wrow, deg, k, copy_path, rng_key, (uint64_t)i, lane,
+                                        w_idx, w_key, emit);
   }
 }
 
@@ -509,65 +306,3 @@ extern "C" int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Whole-batch driver: every hop's sample + relabel is enqueued back to back with device-side
-// seed / edge counts, so a multi-hop batch costs no host round trip until the caller reads the
-// 2*L counts.  Replaces the layer loops P2PCacheNodeClassificationSample{Uniform,Bias}
-// (src/sampling/sampler.cc:14-62), which sync twice per hop.
-extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
-                                 int num_layers, const int64_t *fan_out, int replace,
-                                 uint64_t rng_seed, void *const *out_frontier,
-                                 void *const *out_row, void *const *out_col,
-                                 const int64_t *cap_edges, const int64_t *cap_frontier,
-                                 int64_t *counts_dev, void *sample_ws, void *relabel_table,
-                                 int64_t relabel_capacity, void *relabel_ws, void *stream) {
-  DGS_REQUIRE(g && fan_out && out_frontier && out_row && out_col && cap_edges && cap_frontier &&
-                  counts_dev && sample_ws && relabel_table && relabel_ws,
-              "dgs_sample_blocks: null argument");
-  DGS_REQUIRE(num_layers >= 1 && num_layers <= 16, "dgs_sample_blocks: 1..16 layers supported");
-  DGS_REQUIRE(num_seeds >= 0, "dgs_sample_blocks: negative seed count");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (num_seeds == 0) {
-    DGS_CUDA_OK(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 2 * num_layers, st));
-    return 0;
-  }
-  const void *cur_seeds = seeds;
-  int64_t cur_ub = num_seeds;
-  const int64_t *cur_count_dev = nullptr;
-  for (int l = 0; l < num_layers; ++l) {
-    // the fan-out list is walked from the back, like the reference (sampler.cc:20) and DGL
-    const int64_t k = fan_out[num_layers - 1 - l];
-    DGS_REQUIRE(k >= 0, "dgs_sample_blocks: fan_out must be >= 0 here (use the per-hop entry for "
-                "-1 / full neighbourhoods)");
-    const int64_t nnz_ub = cur_ub * k;
-    DGS_REQUIRE(cap_edges[l] >= nnz_ub, "dgs_sample_blocks: layer %d edge capacity %lld < %lld", l,
-                (long long)cap_edges[l], (long long)nnz_ub);
-    DGS_REQUIRE(cap_frontier[l] >= cur_ub + nnz_ub,
-                "dgs_sample_blocks: layer %d frontier capacity %lld < %lld", l,
-                (long long)cap_frontier[l], (long long)(cur_ub + nnz_ub));
-    DGS_REQUIRE(relabel_capacity >= 2 * (cur_ub + nnz_ub),
-                "dgs_sample_blocks: relabel table too small for layer %d", l);
-    int64_t *nnz_dev = counts_dev + 2 * l;
-    int64_t *nfront_dev = counts_dev + 2 * l + 1;
-    // distinct Philox key per hop
-    const uint64_t key = rng_seed + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
-    int rc = dgs_sample_neighbors(g, cur_seeds, cur_ub, cur_count_dev, k, replace, key, out_row[l],
-                                  out_col[l], cap_edges[l], nnz_dev, sample_ws, stream);
-    if (rc) return rc;
-    const void *map_ptrs[2] = {cur_seeds, out_col[l]};
-    const int64_t map_counts[2] = {cur_ub, nnz_ub};
-    const int64_t *map_counts_dev[2] = {cur_count_dev, nnz_dev};
-    const void *rel_ptrs[2] = {out_row[l], out_col[l]};
-    const int64_t rel_counts[2] = {nnz_ub, nnz_ub};
-    const int64_t *rel_counts_dev[2] = {nnz_dev, nnz_dev};
-    void *rel_out[2] = {out_row[l], out_col[l]};  // relabelled in place
-    rc = dgs_relabel(g->itype, 2, map_ptrs, map_counts, map_counts_dev, 2, rel_ptrs, rel_counts,
-                     rel_counts_dev, rel_out, out_frontier[l], nfront_dev, relabel_table,
-                     relabel_capacity, relabel_ws, stream);
-    if (rc) return rc;
-    cur_seeds = out_frontier[l];
-    cur_ub = cur_ub + nnz_ub;
-    cur_count_dev = nfront_dev;
-  }
-  return 0;
-}

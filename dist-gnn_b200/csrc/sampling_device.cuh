@@ -1,0 +1,240 @@
+// sampling_device.cuh - warp-level neighbour selection shared by the per-hop sampler
+// (sampling.cu) and the fused whole-batch pipeline (blocks.cu).
+#pragma once
+#include "dgs_common.cuh"
+
+namespace dgsb {
+
+struct GraphSrc {
+  const void *indptr;
+  const void *indices;
+  const float *probs;
+  PtrTable sh_indptr, sh_indices, sh_probs;
+  const LocSlot *loc;
+  uint64_t cap_mask;
+};
+
+enum PickMode { kUniform = 0, kUniformReplace = 1, kBias = 2, kBiasReplace = 3 };
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ uint32_t philox_u32(uint64_t key, uint64_t item, uint32_t draw) {
+  uint4 r = Philox::gen(key, item, (uint64_t)(draw >> 2));
+  const uint32_t c = draw & 3u;
+  return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
+}
+
+// Resolve a seed: owner device (-1 = un-cached source), first edge, degree.
+template <typename ET>
+__device__ __forceinline__ void resolve_seed(const GraphSrc &g, long long nid, int *dev,
+                                             long long *begin, long long *deg) {
+  long long v = -1;
+  if (g.loc != nullptr) v = loc_lookup(g.loc, g.cap_mask, nid);
+  long long b, e;
+  if (v >= 0) {
+    *dev = (int)((v >> kDevShift) & 0xff);
+    const long long idx = v & kIdxMask;
+    const ET *ip = reinterpret_cast<const ET *>(g.sh_indptr.p[*dev]);
+    b = (long long)ip[idx];
+    e = (long long)ip[idx + 1];
+  } else {
+    *dev = -1;
+    const ET *ip = reinterpret_cast<const ET *>(g.indptr);
+    b = (long long)ip[nid];
+    e = (long long)ip[nid + 1];
+  }
+  *begin = b;
+  *deg = e - b;
+}
+
+// Emit the k selected neighbours.  w_idx may alias the memory the emit functor writes (global
+// scratch mode: the first 4 k bytes of the seed's own output slots): chunks are processed from
+// the top and every lane reads its position before any lane writes, so a write for output j only
+// overwrites scratch entries >= j that were already consumed.
+template <typename IdT, bool kPos>
+__device__ __forceinline__ IdT pick_value(const IdT *__restrict__ row, long long p) {
+  return kPos ? (IdT)p : row[p];
+}
+
+template <typename IdT, typename Emit, bool kPos = false>
+__device__ __forceinline__ void emit_picks(const IdT *__restrict__ row, const int *w_idx, int k,
+                                           int lane, Emit &emit) {
+  for (int j0 = ((k - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+    const int j = j0 + lane;
+    int p = 0;
+    if (j < k) p = w_idx[j];
+    __syncwarp();
+    if (j < k) emit(j, pick_value<IdT, kPos>(row, p));
+    __syncwarp();
+  }
+}
+
+// One warp selects the neighbours of one seed and hands (output slot j, neighbour id) pairs to
+// `emit` (called by the lane that owns slot j).  copy_path: all `deg` neighbours in CSR order.
+// w_idx / w_key: per-warp scratch of k ints (+ k floats for kBias) when k > 32 or MODE == kBias.
+// kPos: hand the POSITION inside the row to `emit` instead of the neighbour id (no row loads here).
+template <typename IdT, int MODE, typename Emit, bool kPos = false>
+__device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
+                                            const float *__restrict__ wrow, int deg, int k,
+                                            bool copy_path, uint64_t rng_key, uint64_t item,
+                                            int lane, int *w_idx, float *w_key, Emit &emit) {
+  if (copy_path) {
+    // CSR-order copy, 4 independent loads in flight per lane
+    int j = lane;
+    for (; j + 96 < deg; j += 128) {
+      IdT a = pick_value<IdT, kPos>(row, j), b = pick_value<IdT, kPos>(row, j + 32),
+          c = pick_value<IdT, kPos>(row, j + 64), d = pick_value<IdT, kPos>(row, j + 96);
+      emit(j, a); emit(j + 32, b); emit(j + 64, c); emit(j + 96, d);
+    }
+    for (; j < deg; j += 32) emit(j, pick_value<IdT, kPos>(row, j));
+    return;
+  }
+
+  if (MODE == kUniformReplace) {
+    for (int j = lane; j < k; j += 32) {
+      uint32_t p = rand_below(philox_u32(rng_key, item, (uint32_t)j), (uint32_t)deg);
+      emit(j, pick_value<IdT, kPos>(row, p));
+    }
+  } else if (MODE == kUniform) {
+    // Floyd: for t = 0..k-1, J = deg-k+t: r = U[0, J]; pick (r already chosen ? J : r)
+    if (k <= 32) {
+      uint32_t r_mine = 0;
+      if (lane < k)
+        r_mine = rand_below(philox_u32(rng_key, item, (uint32_t)lane),
+                            (uint32_t)(deg - k + lane + 1));
+      uint32_t mine = 0xffffffffu;  // lane t holds the t-th pick
+      for (int t = 0; t < k; ++t) {
+        const uint32_t r = __shfl_sync(0xffffffffu, r_mine, t);
+        const bool dup = __any_sync(0xffffffffu, lane < t && mine == r);
+        if (lane == t) mine = dup ? (uint32_t)(deg - k + t) : r;
+      }
+      if (lane < k) emit(lane, pick_value<IdT, kPos>(row, mine));
+    } else {
+      for (int t0 = 0; t0 < k; t0 += 32) {
+        const int t_mine = t0 + lane;
+        uint32_t r_mine = 0;
+        if (t_mine < k)
+          r_mine = rand_below(philox_u32(rng_key, item, (uint32_t)t_mine),
+                              (uint32_t)(deg - k + t_mine + 1));
+        const int lim = min(32, k - t0);
+        for (int tt = 0; tt < lim; ++tt) {
+          const int t = t0 + tt;
+          const uint32_t r = __shfl_sync(0xffffffffu, r_mine, tt);
+          bool found = false;
+          for (int c = lane; c < t; c += 32) found |= ((uint32_t)w_idx[c] == r);
+          const bool dup = __any_sync(0xffffffffu, found);
+          if (lane == 0) w_idx[t] = dup ? (deg - k + t) : (int)r;
+          __syncwarp();
+        }
+      }
+      emit_picks<IdT, Emit, kPos>(row, w_idx, k, lane, emit);
+    }
+  } else if (MODE == kBias) {
+    // fill the reservoir with the first k items
+    for (int t = lane; t < k; t += 32) {
+      const float w = wrow[t];
+      const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
+      w_key[t] = w > 0.f ? __log2f(u) / w : -INFINITY;
+      w_idx[t] = t;
+    }
+    __syncwarp();
+    // (min key, its slot) over the reservoir
+    float lmin = INFINITY;
+    int lslot = -1;
+    for (int c = lane; c < k; c += 32) {
+      const float v = w_key[c];
+      if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
+    }
+    float wmin = lmin;
+    int wslot = lslot;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+      const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+      if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
+    }
+    for (int t0 = k; t0 < deg; t0 += 32) {
+      const int t = t0 + lane;
+      float key = -INFINITY;
+      if (t < deg) {
+        const float w = wrow[t];
+        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
+        key = w > 0.f ? __log2f(u) / w : -INFINITY;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float ck = __shfl_sync(0xffffffffu, key, src);
+        const int ci = t0 + src;
+        if (ck > wmin) {  // warp-uniform
+          if (lane == 0) { w_key[wslot] = ck; w_idx[wslot] = ci; }
+          __syncwarp();
+          lmin = INFINITY;
+          lslot = -1;
+          for (int c = lane; c < k; c += 32) {
+            const float v = w_key[c];
+            if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
+          }
+          wmin = lmin;
+          wslot = lslot;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+            const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+            if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    emit_picks<IdT, Emit, kPos>(row, w_idx, k, lane, emit);
+  } else {  // kBiasReplace
+    // pass 1: total weight, with exactly the arithmetic of pass 2
+    float total = 0.f;
+    for (int c = 0; c < deg; c += 32) {
+      float w = (c + lane < deg) ? fmaxf(wrow[c + lane], 0.f) : 0.f;
+      float inc = warp_inclusive_scan<float>(w, lane);
+      total = total + __shfl_sync(0xffffffffu, inc, 31);
+    }
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int j = j0 + lane;
+      const bool live = j < k;
+      float thr = 0.f;
+      if (live) thr = u32_to_unit(philox_u32(rng_key, item, (uint32_t)j)) * total;
+      int mypos = deg - 1;  // u == 1 / rounding: clamp like MIN(item, deg - 1), :212
+      bool done = !live;
+      float running = 0.f;
+      for (int c = 0; c < deg; c += 32) {
+        float w = (c + lane < deg) ? fmaxf(wrow[c + lane], 0.f) : 0.f;
+        float inc = warp_inclusive_scan<float>(w, lane);
+        const float cdf = running + inc;
+        const float chunk_end = running + __shfl_sync(0xffffffffu, inc, 31);
+        unsigned mask = __ballot_sync(0xffffffffu, !done && thr < chunk_end);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float r = __shfl_sync(0xffffffffu, thr, src);
+          const unsigned b = __ballot_sync(0xffffffffu, cdf > r);
+          if (lane == src) {
+            mypos = c + __ffs(b) - 1;
+            done = true;
+          }
+        }
+        running = chunk_end;
+        if (__all_sync(0xffffffffu, done)) break;
+      }
+      if (live) emit(j, pick_value<IdT, kPos>(row, mypos));
+    }
+  }
+}
+
+}  // namespace dgsb

@@ -5,7 +5,8 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._util import (check_cpu, check_cuda, contiguous, itype, ptr, stream, tensor_from_ptr, zero_ws)
+from ._util import (ID_DTYPES, check_cpu, check_cuda, contiguous, itype, ptr, stream,
+                    tensor_from_ptr, zero_ws)
 
 lib = _lib.lib
 check = _lib.check
@@ -159,33 +160,47 @@ def _host_source(t, name, all_cached):
 
 
 class _BlockPipeline:
-    """Multi-hop sample + relabel over one dgs_graph_t with persistent workspaces: every hop is
-    enqueued with device-side counts (dgs_sample_blocks) and the host reads the 2 L counts once."""
+    """Multi-hop sample + relabel over one dgs_graph_t: every hop is enqueued with device-side
+    counts (dgs_sample_blocks, 3 kernels per hop) and the host reads the 2 L counts once.
+    Workspaces (incl. the two alternating relabel tables) are cached per (batch, fan-out)."""
 
     def __init__(self, graph, device, id_dtype):
         self._graph = graph
         self._device = device
         self._id_dtype = id_dtype
-        self._ws = None          # sampling workspace
-        self._rl_table = None    # persistent relabel table (kept all-0xFF between calls)
-        self._rl_ws = None
-        self._rl_cap = 0
-        self._rl_items = 0
-        self._max_seeds = 0
-        self._counts_host = None
+        self._plans = {}
 
-    def _reserve(self, max_seeds, max_items):
-        l = lib()
-        if self._ws is None or max_seeds > self._max_seeds:
-            self._ws = zero_ws(l.dgs_sample_ws_bytes(max_seeds), self._device)
-            self._max_seeds = max_seeds
-        cap = l.dgs_relabel_table_capacity(max_items)
-        if self._rl_table is None or cap > self._rl_cap:
-            self._rl_table = torch.full((cap * 2,), -1, dtype=torch.int64, device=self._device)
-            self._rl_cap = cap
-        if self._rl_ws is None or max_items > self._rl_items:
-            self._rl_ws = zero_ws(l.dgs_relabel_ws_bytes(max_items), self._device)
-            self._rl_items = max_items
+    def _plan(self, S, fan_out):
+        key = (S, tuple(fan_out))
+        pl = self._plans.get(key)
+        if pl is None:
+            l = lib()
+            L = len(fan_out)
+            ubs, nnz_ubs = [], []
+            ub = S
+            for li in range(L):
+                k = fan_out[L - 1 - li]
+                ubs.append(ub)
+                nnz_ubs.append(ub * k)
+                ub = ub + ub * k
+            total = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
+            pl = {"L": L, "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "ws": None}
+            if total <= MAX_FUSED_ELEMS:
+                fo = _lib.i64_array(fan_out)
+                it = ID_DTYPES[self._id_dtype]
+                nbytes = l.dgs_sample_blocks_ws_bytes(it, S, L, fo)
+                if nbytes < 0:
+                    raise RuntimeError("sample_blocks: " + l.dgs_last_error().decode())
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
+                check(l.dgs_sample_blocks_ws_init(ptr(ws), nbytes, it, S, L, fo, stream()),
+                      "sample_blocks_ws_init")
+                pl.update(ws=ws, ws_bytes=int(nbytes), fo=fo, epoch=0, cap_edges=_lib.i64_array(nnz_ubs),
+                          cap_front=_lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
+                          counts_host=torch.empty(2 * L, dtype=torch.int64).pin_memory())
+            if len(self._plans) > 8:
+                self._plans.clear()
+            self._plans[key] = pl
+        return pl
 
     def sample(self, seeds, fan_out, replace=False, rng_seed=None):
         l = lib()
@@ -203,39 +218,31 @@ class _BlockPipeline:
             return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
         with torch.cuda.device(self._device):
             S = seeds.numel()
-            ubs, nnz_ubs = [], []
-            ub = S
-            for li in range(L):
-                k = fan_out[L - 1 - li]
-                ubs.append(ub)
-                nnz_ubs.append(ub * k)
-                ub = ub + ub * k
-            total = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
-            if total > MAX_FUSED_ELEMS:
+            pl = self._plan(S, fan_out)
+            if pl["ws"] is None:
                 # worst-case buffers would be unreasonable (huge fan-out used as "all neighbours"):
                 # size every hop exactly instead, at the price of a host sync per hop
                 return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
-            self._reserve(max(ubs), ub)
-            arena = torch.empty(total, dtype=seeds.dtype, device=self._device)
+            arena = torch.empty(pl["total"], dtype=seeds.dtype, device=self._device)
             fr, rows, cols = [], [], []
             off = 0
-            for u, n in zip(ubs, nnz_ubs):
+            for u, n in zip(pl["ubs"], pl["nnz_ubs"]):
                 fr.append(arena[off:off + u + n]); off += u + n
                 rows.append(arena[off:off + n]); off += n
                 cols.append(arena[off:off + n]); off += n
+            es = arena.element_size()
+            base = arena.data_ptr()
             counts_dev = torch.empty(2 * L, dtype=torch.int64, device=self._device)
             check(l.dgs_sample_blocks(
-                C.byref(self._graph), ptr(seeds), S, L, _lib.i64_array(fan_out),
-                int(bool(replace)), C.c_uint64(rng_seed),
-                _lib.vp_array([t.data_ptr() for t in fr]),
-                _lib.vp_array([t.data_ptr() if t.numel() else None for t in rows]),
-                _lib.vp_array([t.data_ptr() if t.numel() else None for t in cols]),
-                _lib.i64_array(nnz_ubs), _lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
-                ptr(counts_dev), ptr(self._ws), ptr(self._rl_table), self._rl_cap,
-                ptr(self._rl_ws), stream()), "sample_blocks")
-            if self._counts_host is None or self._counts_host.numel() < 2 * L:
-                self._counts_host = torch.empty(2 * L, dtype=torch.int64).pin_memory()
-            ch = self._counts_host[:2 * L]
+                C.byref(self._graph), seeds.data_ptr(), S, L, pl["fo"], int(bool(replace)),
+                C.c_uint64(rng_seed),
+                _lib.vp_array([base + t.storage_offset() * es for t in fr]),
+                _lib.vp_array([base + t.storage_offset() * es for t in rows]),
+                _lib.vp_array([base + t.storage_offset() * es for t in cols]),
+                pl["cap_edges"], pl["cap_front"], counts_dev.data_ptr(), pl["ws"].data_ptr(),
+                pl["ws_bytes"], pl["epoch"], stream()), "sample_blocks")
+            pl["epoch"] += 1
+            ch = pl["counts_host"]
             ch.copy_(counts_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the only host sync of the batch
             counts = ch.tolist()

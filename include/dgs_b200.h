@@ -166,19 +166,27 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
                          int64_t *out_nnz_dev, void *ws, void *stream);
 
 /* Whole mini-batch: num_layers hops (fan_out walked from the back, like the reference's
- * sampler.cc:20 and DGL), each hop sampled and relabelled (in place: out_row / out_col come back
- * as positions in out_frontier[l]); hop l+1's seeds are hop l's frontier.  Everything is enqueued
+ * sampler.cc:20 and DGL), each hop sampled and relabelled: out_row / out_col are positions in
+ * out_frontier[l], hop l+1's seeds are hop l's frontier.  3 kernels per hop + 1, all enqueued
  * with device-side counts; the caller reads counts_dev = {nnz_0, |frontier_0|, nnz_1, ...} (2 L
  * int64) once at the end.  Replaces P2PCacheNodeClassificationSample{Uniform,Bias}
- * (src/sampling/sampler.cc:14-62).  Capacities: cap_edges[l] >= ub_l * k_l,
- * cap_frontier[l] >= ub_l * (1 + k_l) with ub_0 = num_seeds, ub_{l+1} = ub_l * (1 + k_l);
- * relabel_capacity >= 2 * max_l ub_{l+1}. */
+ * (src/sampling/sampler.cc:14-62).  fan_out[i] >= 0 here.
+ * Capacities: cap_edges[l] >= ub_l * k_l, cap_frontier[l] >= ub_l * (1 + k_l) with
+ * ub_0 = num_seeds, ub_{l+1} = ub_l * (1 + k_l).
+ * ws: dgs_sample_blocks_ws_bytes(...) bytes, initialised ONCE with dgs_sample_blocks_ws_init for
+ * the same (itype, num_seeds, num_layers, fan_out); epoch = number of dgs_sample_blocks calls
+ * already made on this workspace since its init (0, 1, 2, ...): the relabel table a call leaves
+ * dirty is wiped by the first kernel of the next call, which needs to know which of the two
+ * alternating tables that is.  3 kernels per hop, no memset, no trailing clean-up launch. */
+int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
+                                   const int64_t *fan_out);
+int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
+                              int num_layers, const int64_t *fan_out, void *stream);
 int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds, int num_layers,
                       const int64_t *fan_out, int replace, uint64_t rng_seed,
                       void *const *out_frontier, void *const *out_row, void *const *out_col,
                       const int64_t *cap_edges, const int64_t *cap_frontier, int64_t *counts_dev,
-                      void *sample_ws, void *relabel_table, int64_t relabel_capacity,
-                      void *relabel_ws, void *stream);
+                      void *ws, int64_t ws_bytes, int64_t epoch, void *stream);
 
 /* ------------------------------------------------------------------ relabel
  * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):

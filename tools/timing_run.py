@@ -1,0 +1,12 @@
+"""Per-kernel warm timings of the fused pipeline (DGS_BLOCKS_TIMING=1 must be set)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dist-gnn_b200"))
+import torch, dgs, dgs_synth
+dev = torch.device("cuda", 0)
+N, E, D, dt = dgs_synth.SHAPES["products"]
+ip, ix, _ = dgs_synth.make_csr(N, E, device=dev)
+sampler = dgs.classes.CSRSampler(ip, ix)
+seeds = dgs_synth.seed_batches(N, 1024, 12, device=dev)
+for i in range(12):
+    sampler._CAPI_sample_node_classifiction(seeds[i], [15, 10, 5])
