@@ -25,7 +25,9 @@
 // The result is bit-identical to sample -> TensorRelabelCUDA({seeds, col}, {row, col}): `frontier`
 // is the first-occurrence-order unique of cat(seeds, coo_col), the COO is seed-major with the
 // neighbours of a seed in selection order (CSR order on the copy path).
+#include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -33,7 +35,13 @@
 #include "p2p_server.h"
 #include "sampling_device.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace dgsb {
+
+#ifndef DGS_COOP_MIN_CTAS
+#define DGS_COOP_MIN_CTAS 2  // measured on B200: 2 CTAs/SM (128 regs, no spills) beats 3 and 4
+#endif
 
 constexpr int kBkWarps = 8;
 constexpr int kBkThreads = 256;
@@ -173,16 +181,24 @@ __device__ __forceinline__ void rl_wipe(RlSlot *table, unsigned int pos) {
 }
 
 // wipe every slot the given hop touched (idempotent; duplicates wipe the same slot twice)
-__device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = tid; i < S; i += stride) rl_wipe(h.table, h.pos_seed[i]);
+// busy_ctas: CTAs [0, busy_ctas) have sampling work of their own in this phase; when enough idle
+// CTAs exist the wipe is left to them alone (it then overlaps the sampling chains entirely).
+__device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k, int64_t busy_ctas = 0) {
+  int64_t vgrid = gridDim.x, vbid = blockIdx.x;
+  if (busy_ctas < (int64_t)gridDim.x && (int64_t)gridDim.x - busy_ctas >= 64) {
+    if ((int64_t)blockIdx.x < busy_ctas) return;
+    vgrid = (int64_t)gridDim.x - busy_ctas;
+    vbid = (int64_t)blockIdx.x - busy_ctas;
+  }
+  const int64_t stride = vgrid * blockDim.x;
+  const int64_t tid = vbid * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < S; i += stride) rl_wipe(h.table, __ldcg(h.pos_seed + i));
   if (k > 0) {
     const int64_t E = S * k;
     for (int64_t e = tid; e < E; e += stride) {
       const int64_t i = e / k;
       const int j = (int)(e - i * k);
-      if (j < h.cnt[i]) rl_wipe(h.table, h.pos_col[e]);
+      if (j < __ldcg(h.cnt + i)) rl_wipe(h.table, __ldcg(h.pos_col + e));
     }
   }
 }
@@ -207,12 +223,7 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
                   HopState cur, uint64_t cap_mask, HopState prev, int64_t prev_S_ub,
                   const long long *__restrict__ prev_S_dev, int prev_k, int gmem_scratch) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
-  // (1) wipe the other table: the slots the previous hop touched
-  if (prev.table != nullptr) {
-    const int64_t pS = min((int64_t)*prev_S_dev, prev_S_ub);
-    wipe_hop(prev, pS, prev_k);
-  }
-  // (2) sample this hop
+  const long long pS_live = prev.table != nullptr ? *prev_S_dev : 0;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
@@ -255,19 +266,32 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
     warp_select<IdT, MODE, PadEmit<IdT>>(row, wrow, deg, k, copy_path, rng_key, (uint64_t)i, lane,
                                         w_idx, w_key, emit);
   }
+  // wipe the other table: the slots the previous hop touched
+  if (prev.table != nullptr) wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k);
 }
 
 
 // ---------------------------------------------------------------------------------------------
-// Tile version of fused_pick (num_picks small enough for shared memory): a CTA owns 128 seeds.
-//   A  thread per seed : probe, indptr pair, count, insert the seed id        (128 chains in flight)
-//   B1 warp per seed   : selection -> POSITIONS inside the row, kept in shared memory (no loads
-//                        for uniform sampling; the weight scan for biased sampling)
-//   B2 thread per slot : neighbour load, padded store, table insert           (every slot of the
-//                        tile is an independent load -> CAS -> atomicMin chain)
-// The warp-per-seed kernel above serialises these chains per seed; here the memory-level
-// parallelism is the tile's whole edge set.  Same RNG counters => identical samples.
-constexpr int kPkSeeds = 128;
+// Phase functions.  Each is written as a loop over tiles / slots strided by the grid, so the same
+// code runs as a stand-alone kernel (multi-kernel path) or as one phase of the cooperative
+// whole-batch kernel (phases separated by grid barriers).  Data produced by other CTAs in an
+// earlier phase is read with ld.global.cg (L2), never through a possibly stale L1 line.
+constexpr int kPkSeeds = 128;  // seeds per pick tile
+constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick / emit phases
+constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
+
+template <typename T>
+__device__ __forceinline__ T ldcg(const T *p) {
+  return __ldcg(p);
+}
+__device__ __forceinline__ RlSlot ldcg_slot(const RlSlot *p) {
+  const int4 raw = __ldcg(reinterpret_cast<const int4 *>(p));
+  RlSlot s;
+  s.key = ((long long)(uint32_t)raw.y << 32) | (uint32_t)raw.x;
+  s.first = (unsigned int)raw.z;
+  s.lrank = (unsigned int)raw.w;
+  return s;
+}
 
 template <typename IdT>
 struct PosEmit {
@@ -275,12 +299,19 @@ struct PosEmit {
   __device__ __forceinline__ void operator()(int j, IdT v) { p[j] = (unsigned int)v; }
 };
 
+// Pick phase, tile version: a CTA owns 128 seeds.
+//   A  thread per seed : probe, indptr pair, count, insert the seed id        (128 chains in flight)
+//   B1 selection -> POSITIONS inside the row, kept in shared memory: Floyd's subset sampling run
+//      by one thread per seed for uniform sampling (no memory traffic at all), a warp per seed
+//      for the weight scans of biased sampling
+//   B2 thread per slot : neighbour load, padded store, table insert - 8 independent
+//      load -> CAS chains in flight per thread
+// Same RNG counters as the warp-per-seed kernel => identical samples.
 template <typename IdT, typename ET, int MODE>
-__global__ void __launch_bounds__(kBkThreads)
-fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
-                       const int64_t *__restrict__ S_dev, int k, uint64_t rng_key,
-                       IdT *__restrict__ pad_col, HopState cur, uint64_t cap_mask, HopState prev,
-                       int64_t prev_S_ub, const long long *__restrict__ prev_S_dev, int prev_k) {
+__device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__restrict__ seeds,
+                                                int64_t S_ub, int64_t S, int k, uint64_t rng_key,
+                                                IdT *__restrict__ pad_col, const HopState &cur,
+                                                uint64_t cap_mask) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
   __shared__ const IdT *s_row[kPkSeeds];
   __shared__ const float *s_w[kPkSeeds];
@@ -288,21 +319,25 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
   __shared__ int s_cnt[kPkSeeds];
   unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
   float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
-  if (prev.table != nullptr) {
-    const int64_t pS = min((int64_t)*prev_S_dev, prev_S_ub);
-    wipe_hop(prev, pS, prev_k);
-  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
   const int64_t tiles = (S + kPkSeeds - 1) / kPkSeeds;
   const bool with_replace = (MODE == kUniformReplace || MODE == kBiasReplace);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t i0 = tile * kPkSeeds;
     const int ns = (int)min((int64_t)kPkSeeds, S - i0);
     __syncthreads();  // previous tile's readers are done with the shared arrays
+    long long seed_nid = 0;
+    uint64_t seed_pos = 0;
+    unsigned long long seed_prev = 0;
     if (tid < ns) {
       const int64_t i = i0 + tid;
-      const long long nid = (long long)seeds[i];
+      const long long nid = (long long)ldcg(seeds + i);
+      // first probe of the seed's own table insert: issued now, resolved after the neighbours'
+      // (its round trip overlaps the indptr loads, the selection and the row loads)
+      seed_nid = nid;
+      seed_pos = mix64((uint64_t)nid) & cap_mask;
+      seed_prev = atomicCAS((unsigned long long *)&cur.table[seed_pos].key,
+                            (unsigned long long)kEmptyKey, (unsigned long long)nid);
       int dev;
       long long begin, deg64;
       resolve_seed<ET>(g, nid, &dev, &begin, &deg64);
@@ -314,23 +349,32 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
       s_deg[tid] = deg;
       s_cnt[tid] = cnt;
       cur.cnt[i] = cnt;
-      cur.pos_seed[i] = rl_insert(cur.table, cap_mask, nid, (unsigned int)i);
+    }
+    if (MODE == kUniform) {
+      // random words of Floyd's draws, computed by all threads (one Philox block = 4 draws)
+      const int blocks_per_seed = (k + 3) >> 2;
+      for (int b = tid; b < ns * blocks_per_seed; b += kBkThreads) {
+        const int si = b / blocks_per_seed, q = b - si * blocks_per_seed;
+        const uint4 r4 = Philox::gen(rng_key, (uint64_t)(i0 + si), (uint64_t)q);
+        unsigned int *P = s_pick + (size_t)si * k + 4 * q;
+        const int left = k - 4 * q;
+        P[0] = r4.x;
+        if (left > 1) P[1] = r4.y;
+        if (left > 2) P[2] = r4.z;
+        if (left > 3) P[3] = r4.w;
+      }
     }
     __syncthreads();
-    // B1: positions of the sampled rows
     if (MODE == kUniform) {
-      // Floyd's subset sampling, one THREAD per seed (k draws, O(k^2) compares against the
-      // positions already in shared memory): the whole tile is selected in one short burst
+      // Floyd's subset sampling, one THREAD per seed: draw t picks r in [0, deg-k+t], or deg-k+t
+      // itself when r was already picked (O(k^2) compares against shared memory, no traffic)
       if (tid < ns) {
         const int deg = s_deg[tid];
         if (deg > k) {
           unsigned int *P = s_pick + (size_t)tid * k;
-          uint4 r4 = make_uint4(0, 0, 0, 0);
           for (int t = 0; t < k; ++t) {
-            if ((t & 3) == 0) r4 = Philox::gen(rng_key, (uint64_t)(i0 + tid), (uint64_t)(t >> 2));
-            const uint32_t rr = (t & 3) == 0 ? r4.x : ((t & 3) == 1 ? r4.y : ((t & 3) == 2 ? r4.z : r4.w));
             const unsigned int J = (unsigned int)(deg - k + t);
-            const unsigned int r = rand_below(rr, J + 1);
+            const unsigned int r = rand_below(P[t], J + 1);
             bool dup = false;
             for (int q = 0; q < t; ++q) dup |= (P[q] == r);
             P[t] = dup ? J : r;
@@ -349,14 +393,13 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
       }
     }
     __syncthreads();
-    // B2: one slot per thread; 4 independent row loads, then 4 independent table inserts in flight
     const int slots = ns * k;
-    for (int base = tid; base < slots; base += kBkThreads * 4) {
-      long long v[4];
-      unsigned int item[4], pos[4];
-      bool ok[4];
+    for (int base = tid; base < slots; base += kBkThreads * kPkBatch) {
+      long long v[kPkBatch];
+      unsigned int item[kPkBatch], pos[kPkBatch];
+      bool ok[kPkBatch];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kPkBatch; ++u) {
         const int el = base + u * kBkThreads;
         ok[u] = false;
         v[u] = 0;
@@ -376,9 +419,9 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
           }
         }
       }
-      rl_insert_batch<4>(cur.table, cap_mask, v, item, ok, pos);
+      rl_insert_batch<kPkBatch>(cur.table, cap_mask, v, item, ok, pos);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kPkBatch; ++u) {
         if (ok[u]) {
           const int64_t e = i0 * k + (base + u * kBkThreads);
           pad_col[e] = (IdT)v[u];
@@ -386,45 +429,46 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
         }
       }
     }
+    if (tid < ns) {
+      while (seed_prev != (unsigned long long)kEmptyKey && seed_prev != (unsigned long long)seed_nid) {
+        seed_pos = (seed_pos + 1) & cap_mask;
+        seed_prev = atomicCAS((unsigned long long *)&cur.table[seed_pos].key,
+                              (unsigned long long)kEmptyKey, (unsigned long long)seed_nid);
+      }
+      atomicMin(&cur.table[seed_pos].first, (unsigned int)(i0 + tid));
+      cur.pos_seed[i0 + tid] = (unsigned int)seed_pos;
+    }
   }
 }
 
-constexpr int kRkItems = 8;  // padded slots per thread and pass (blocked arrangement)
-
-__global__ void __launch_bounds__(kBkThreads)
-fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopState cur,
-                  BlocksWs ws, int64_t *__restrict__ out_nnz, int64_t *__restrict__ out_nfront) {
+// Rank phase: CTA per 64 seeds - flags first occurrences among the seeds (A) and the sampled
+// neighbours (B), counts the edges (C), block scans, per-tile totals to prefA / prefB / prefC.
+__device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k, const HopState &cur,
+                                                 const BlocksWs &ws) {
   __shared__ long long s_scan[32];
   __shared__ long long s_total;
   __shared__ int s_cnt[kBkTile];
-  __shared__ bool s_last;
-  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
   const int64_t tiles = (S + kBkTile - 1) / kBkTile;
   const int tid = threadIdx.x;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t i0 = tile * kBkTile;
     const int ns = (int)min((int64_t)kBkTile, S - i0);
+    const int items = ns * k;
+    const int64_t e0 = i0 * k;
     __syncthreads();
-    // A: first occurrences among the tile's seeds, C: its edge count - one packed scan
+    // first wave of loads: seed slot + count, and the first pass of neighbour slots
     long long fa = 0, c = 0;
     unsigned int slot_a = 0;
     if (tid < ns) {
-      slot_a = cur.pos_seed[i0 + tid];
-      c = cur.cnt[i0 + tid];
+      slot_a = ldcg(cur.pos_seed + i0 + tid);
+      c = ldcg(cur.cnt + i0 + tid);
       s_cnt[tid] = (int)c;
-      fa = (cur.table[slot_a].first == (unsigned int)(i0 + tid)) ? 1 : 0;
     }
-    const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
-    const long long totA = s_total >> 32, totC = s_total & 0xffffffffll;
-    if (fa) cur.table[slot_a].lrank = (unsigned int)(rac >> 32);
-    if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
-    // B: first occurrences among the tile's sampled neighbours.  The tile's padded slots are
-    // contiguous (e = i0 k + el); every thread owns kRkItems consecutive slots, issues all its
-    // table probes first, then one block scan ranks the whole pass.
+    __syncthreads();
+    if (tid < ns) fa = (ldcg(&cur.table[slot_a].first) == (unsigned int)(i0 + tid)) ? 1 : 0;
     long long carry = 0;
-    const int items = ns * k;
-    const int64_t e0 = i0 * k;
-    for (int base = 0; base < items; base += kBkThreads * kRkItems) {
+    long long totA = 0, totC = 0;
+    for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
       const int el0 = base + tid * kRkItems;
       unsigned int slot[kRkItems];
       bool valid[kRkItems];
@@ -435,13 +479,21 @@ fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopSta
         if (el < items) {
           const int si = el / k;
           valid[u] = (el - si * k) < s_cnt[si];
-          if (valid[u]) slot[u] = cur.pos_col[e0 + el];
+          if (valid[u]) slot[u] = ldcg(cur.pos_col + e0 + el);
         }
       }
       unsigned int first[kRkItems];
 #pragma unroll
       for (int u = 0; u < kRkItems; ++u)
-        if (valid[u]) first[u] = cur.table[slot[u]].first;
+        if (valid[u]) first[u] = ldcg(&cur.table[slot[u]].first);
+      if (base == 0) {
+        // A and C share one packed scan (A in the high half)
+        const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
+        totA = s_total >> 32;
+        totC = s_total & 0xffffffffll;
+        if (fa) cur.table[slot_a].lrank = (unsigned int)(rac >> 32);
+        if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
+      }
       int mine = 0;
       bool fb[kRkItems];
 #pragma unroll
@@ -461,55 +513,151 @@ fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopSta
       ws.prefC[tile] = totC;
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    unsigned int t = atomicAdd(ws.done, 1u);
-    s_last = (t == gridDim.x - 1);
+}
+
+// Executed by ONE CTA after every tile total is visible: exclusive scans of the three per-tile
+// totals (every thread owns a run of consecutive tiles), publishes nnz and |frontier|.
+__device__ __forceinline__ void rank_tail(int64_t S, const BlocksWs &ws, long long *out_nnz,
+                                          long long *out_nfront) {
+  __shared__ long long t_scan[32];
+  __shared__ long long t_total;
+  const int tid = threadIdx.x;
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  volatile long long *pa = ws.prefA, *pb = ws.prefB, *pc = ws.prefC;
+  const int64_t per = (tiles + kBkThreads - 1) / kBkThreads;
+  const int64_t t0 = min(tiles, (int64_t)tid * per), t1 = min(tiles, t0 + per);
+  long long sa = 0, sb = 0, sc = 0;
+  for (int64_t t = t0; t < t1; ++t) {
+    sa += pa[t];
+    sb += pb[t];
+    sc += pc[t];
   }
-  __syncthreads();
-  if (s_last) {
-    // exclusive scans of the three per-tile totals: every thread owns a run of consecutive tiles
-    __threadfence();
-    volatile long long *pa = ws.prefA, *pb = ws.prefB, *pc = ws.prefC;
-    const int64_t per = (tiles + kBkThreads - 1) / kBkThreads;
-    const int64_t t0 = (int64_t)tid * per, t1 = min(tiles, t0 + per);
-    long long sa = 0, sb = 0, sc = 0;
-    for (int64_t t = t0; t < t1; ++t) {
-      sa += pa[t];
-      sb += pb[t];
-      sc += pc[t];
-    }
-    long long xa = block_exclusive_scan<long long>(sa, s_scan, &s_total);
-    const long long totA = s_total;
-    long long xb = block_exclusive_scan<long long>(sb, s_scan, &s_total);
-    const long long totB = s_total;
-    long long xc = block_exclusive_scan<long long>(sc, s_scan, &s_total);
-    const long long totC = s_total;
-    for (int64_t t = t0; t < t1; ++t) {
-      const long long va = pa[t], vb = pb[t], vc = pc[t];
-      pa[t] = xa; pb[t] = xb; pc[t] = xc;
-      xa += va; xb += vb; xc += vc;
-    }
-    if (tid == 0) {
-      pa[tiles] = totA;
-      pb[tiles] = totB;
-      pc[tiles] = totC;
-      *out_nnz = totC;
-      *out_nfront = totA + totB;
-      *ws.done = 0;
-    }
+  long long xa = block_exclusive_scan<long long>(sa, t_scan, &t_total);
+  const long long totA = t_total;
+  long long xb = block_exclusive_scan<long long>(sb, t_scan, &t_total);
+  const long long totB = t_total;
+  long long xc = block_exclusive_scan<long long>(sc, t_scan, &t_total);
+  const long long totC = t_total;
+  for (int64_t t = t0; t < t1; ++t) {
+    const long long va = pa[t], vb = pb[t], vc = pc[t];
+    pa[t] = xa; pb[t] = xb; pc[t] = xc;
+    xa += va; xb += vb; xc += vc;
+  }
+  if (tid == 0) {
+    pa[tiles] = totA;
+    pb[tiles] = totB;
+    pc[tiles] = totC;
+    *out_nnz = totC;
+    *out_nfront = totA + totB;
   }
 }
 
 // new id of the key stored in `s` (first occurrence f, rank inside its tile)
 __device__ __forceinline__ long long new_id(const RlSlot &s, int64_t S_ub, int k, long long totA,
-                                            const long long *__restrict__ prefA,
-                                            const long long *__restrict__ prefB) {
+                                            const long long *prefA, const long long *prefB) {
   const unsigned int f = s.first;
-  if ((int64_t)f < S_ub) return prefA[f / kBkTile] + (long long)s.lrank;
+  if ((int64_t)f < S_ub) return ldcg(prefA + f / kBkTile) + (long long)s.lrank;
   const int64_t e = (int64_t)f - S_ub;
-  return totA + prefB[(e / k) / kBkTile] + (long long)s.lrank;
+  return totA + ldcg(prefB + (e / k) / kBkTile) + (long long)s.lrank;
+}
+
+// Emit phase: thread per padded slot - frontier[new id] = id for first occurrences, COO written
+// compacted and relabelled.  kPkBatch slots per thread and pass, loads staged level by level.
+template <typename IdT>
+__device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_t S_ub, int64_t S,
+                                           int k, const IdT *__restrict__ pad_col,
+                                           const HopState &cur, const BlocksWs &ws,
+                                           IdT *__restrict__ frontier, IdT *__restrict__ out_row,
+                                           IdT *__restrict__ out_col) {
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  const long long totA = ldcg(ws.prefA + tiles);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) *ws.pending_S = S;  // this hop's table is dirty until the next pick phase wipes it
+  for (int64_t i = tid; i < S; i += stride) {
+    const RlSlot s = ldcg_slot(&cur.table[ldcg(cur.pos_seed + i)]);
+    if (s.first == (unsigned int)i)
+      frontier[ldcg(ws.prefA + i / kBkTile) + (long long)s.lrank] = ldcg(seeds + i);
+  }
+  if (k <= 0) return;
+  const int64_t E = S * k;
+  for (int64_t base = tid; base < E; base += stride * kPkBatch) {
+    int64_t si[kPkBatch];
+    int jj[kPkBatch];
+    bool ok[kPkBatch];
+    unsigned int pc[kPkBatch], ps[kPkBatch];
+#pragma unroll
+    for (int u = 0; u < kPkBatch; ++u) {
+      const int64_t e = base + u * stride;
+      ok[u] = false;
+      if (e < E) {
+        si[u] = e / k;
+        jj[u] = (int)(e - si[u] * k);
+        ok[u] = jj[u] < ldcg(cur.cnt + si[u]);
+        pc[u] = ldcg(cur.pos_col + e);
+        ps[u] = ldcg(cur.pos_seed + si[u]);
+      }
+    }
+    unsigned int cf[kPkBatch], cr[kPkBatch], sf[kPkBatch], sr[kPkBatch];
+#pragma unroll
+    for (int u = 0; u < kPkBatch; ++u) {
+      if (ok[u]) {
+        const int2 c2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[pc[u]].first));
+        const int2 s2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[ps[u]].first));
+        cf[u] = (unsigned int)c2.x; cr[u] = (unsigned int)c2.y;
+        sf[u] = (unsigned int)s2.x; sr[u] = (unsigned int)s2.y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPkBatch; ++u) {
+      if (ok[u]) {
+        const int64_t e = base + u * stride;
+        RlSlot sc;
+        sc.first = cf[u];
+        sc.lrank = cr[u];
+        const long long cid = new_id(sc, S_ub, k, totA, ws.prefA, ws.prefB);
+        if ((int64_t)cf[u] == S_ub + e) frontier[cid] = ldcg(pad_col + e);
+        const long long rid = ldcg(ws.prefA + sf[u] / kBkTile) + (long long)sr[u];
+        const long long o = ldcg(ws.prefC + si[u] / kBkTile) + (long long)ldcg(ws.loff + si[u]) + jj[u];
+        out_row[o] = (IdT)rid;
+        out_col[o] = (IdT)cid;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-kernel path: 3 launches per hop.
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads)
+fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
+                       const int64_t *__restrict__ S_dev, int k, uint64_t rng_key,
+                       IdT *__restrict__ pad_col, HopState cur, uint64_t cap_mask, HopState prev,
+                       int64_t prev_S_ub, const long long *__restrict__ prev_S_dev, int prev_k) {
+  const long long pS_live = *prev_S_dev;
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  pick_tile_phase<IdT, ET, MODE>(g, seeds, S_ub, S, k, rng_key, pad_col, cur, cap_mask);
+  wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + kPkSeeds - 1) / kPkSeeds);
+}
+
+__global__ void __launch_bounds__(kBkThreads)
+fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopState cur,
+                  BlocksWs ws, int64_t *__restrict__ out_nnz, int64_t *__restrict__ out_nfront) {
+  __shared__ bool s_last;
+  const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
+  rank_tiles_phase(S_ub, S, k, cur, ws);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ws.done, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    rank_tail(S, ws, (long long *)out_nnz, (long long *)out_nfront);
+    if (threadIdx.x == 0) *ws.done = 0;
+  }
 }
 
 template <typename IdT>
@@ -518,29 +666,76 @@ fused_emit_kernel(const IdT *__restrict__ seeds, int64_t S_ub, const int64_t *__
                   int k, const IdT *__restrict__ pad_col, HopState cur, BlocksWs ws,
                   IdT *__restrict__ frontier, IdT *__restrict__ out_row, IdT *__restrict__ out_col) {
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
-  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
-  const long long totA = ws.prefA[tiles];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid == 0) *ws.pending_S = S;  // this hop's table is dirty until the next pick kernel wipes it
-  for (int64_t i = tid; i < S; i += stride) {
-    const RlSlot s = cur.table[cur.pos_seed[i]];
-    if (s.first == (unsigned int)i) frontier[ws.prefA[i / kBkTile] + (long long)s.lrank] = seeds[i];
-  }
-  if (k <= 0) return;
-  const int64_t E = S * k;
-  for (int64_t e = tid; e < E; e += stride) {
-    const int64_t i = e / k;
-    const int j = (int)(e - i * k);
-    if (j >= cur.cnt[i]) continue;
-    const RlSlot sc = cur.table[cur.pos_col[e]];
-    const long long cid = new_id(sc, S_ub, k, totA, ws.prefA, ws.prefB);
-    if ((int64_t)sc.first == S_ub + e) frontier[cid] = pad_col[e];
-    const RlSlot ss = cur.table[cur.pos_seed[i]];
-    const long long rid = ws.prefA[ss.first / kBkTile] + (long long)ss.lrank;
-    const long long o = ws.prefC[i / kBkTile] + (long long)ws.loff[i] + j;
-    out_row[o] = (IdT)rid;
-    out_col[o] = (IdT)cid;
+  emit_phase<IdT>(seeds, S_ub, S, k, pad_col, cur, ws, frontier, out_row, out_col);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative whole-batch kernel: every hop's pick / rank / totals / emit as phases of ONE launch,
+// separated by grid barriers - no kernel boundary (launch + drain + ramp, ~3-4 us each at these
+// sizes) and a single CPU-side launch per mini-batch.
+struct HopArgs {
+  const void *seeds;
+  void *frontier, *out_row, *out_col;
+  long long *nnz_dev, *nf_dev;
+  const long long *S_dev;   // live seed count (nullptr: S_ub is exact)
+  int64_t S_ub, prev_S_ub;
+  uint64_t key;
+  int k, prev_k, cur;
+};
+struct BatchArgs {
+  int L;
+  uint64_t cap_mask;
+  unsigned long long *trace;  // debug: %globaltimer stamps of CTA 0 around every phase
+  HopArgs hop[8];
+};
+
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads, DGS_COOP_MIN_CTAS)
+fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  int nt = 0;
+  auto stamp = [&]() {
+    if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[nt++] = t;
+    }
+  };
+  stamp();
+  for (int l = 0; l < a.L; ++l) {
+    const HopArgs &h = a.hop[l];
+    const HopState &cur = ws.hop[h.cur];
+    const HopState &prev = ws.hop[h.cur ^ 1];
+    const long long pS_live = ldcg(ws.pending_S);
+    const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
+    pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
+                                   (IdT *)ws.pad_col, cur, a.cap_mask);
+    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + kPkSeeds - 1) / kPkSeeds);
+    stamp();
+    grid.sync();
+    stamp();
+    rank_tiles_phase(h.S_ub, S, h.k, cur, ws);
+    stamp();
+    {
+      __shared__ bool s_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(ws.done, 1u) == gridDim.x - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        rank_tail(S, ws, h.nnz_dev, h.nf_dev);
+        if (threadIdx.x == 0) *ws.done = 0;
+      }
+    }
+    stamp();
+    grid.sync();
+    stamp();
+    emit_phase<IdT>((const IdT *)h.seeds, h.S_ub, S, h.k, (const IdT *)ws.pad_col, cur, ws,
+                    (IdT *)h.frontier, (IdT *)h.out_row, (IdT *)h.out_col);
+    stamp();
+    grid.sync();
+    stamp();
   }
 }
 
@@ -570,7 +765,85 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
       ub += ub * fan_out[L - 1 - l];
     }
   }
-  // DGS_BLOCKS_TIMING=1: CUDA events after every kernel, printed (and synchronised!) per call
+  // shared memory of the tile pick phase: 128 k positions (+ 8 k keys when biased)
+  size_t smem_max = 0;
+  bool all_tile = true;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[L - 1 - l];
+    size_t sm = (size_t)kPkSeeds * k * sizeof(int) + (mode == kBias ? (size_t)kBkWarps * k * sizeof(float) : 0);
+    DGS_REQUIRE(cap_edges[l] >= ubs[l] * k, "sample_blocks: layer %d edge capacity %lld < %lld", l,
+                (long long)cap_edges[l], (long long)(ubs[l] * k));
+    DGS_REQUIRE(cap_frontier[l] >= ubs[l] * (1 + k),
+                "sample_blocks: layer %d frontier capacity %lld < %lld", l,
+                (long long)cap_frontier[l], (long long)(ubs[l] * (1 + k)));
+    if (k <= 0 || sm > 64 * 1024) all_tile = false;
+    if (sm > smem_max) smem_max = sm;
+  }
+  static const char *mode_env = getenv("DGS_BLOCKS_MODE");  // "multi" forces the 3-kernels-per-hop path
+  const bool want_coop = !(mode_env && strcmp(mode_env, "multi") == 0);
+
+  // ---- cooperative single-launch path
+  if (want_coop && all_tile && L <= 8) {
+    BatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = L;
+    a.cap_mask = cap_mask;
+    for (int l = 0; l < L; ++l) {
+      HopArgs &h = a.hop[l];
+      const int pl = l > 0 ? l - 1 : L - 1;
+      h.seeds = l == 0 ? (const void *)seeds : out_frontier[l - 1];
+      h.frontier = out_frontier[l];
+      h.out_row = out_row[l];
+      h.out_col = out_col[l];
+      h.nnz_dev = (long long *)(counts_dev + 2 * l);
+      h.nf_dev = (long long *)(counts_dev + 2 * l + 1);
+      h.S_dev = l == 0 ? nullptr : (const long long *)(counts_dev + 2 * (l - 1) + 1);
+      h.S_ub = ubs[l];
+      h.prev_S_ub = ubs[pl];
+      h.key = rng_seed + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
+      h.k = (int)fan_out[L - 1 - l];
+      h.prev_k = (int)fan_out[L - 1 - pl];
+      h.cur = (int)((epoch * L + l) & 1);
+    }
+    void *kern = nullptr;
+#define DGS_BK(M) kern = (void *)fused_batch_kernel<IdT, ET, M>
+    switch (mode) {
+      case kUniform: DGS_BK(kUniform); break;
+      case kUniformReplace: DGS_BK(kUniformReplace); break;
+      case kBias: DGS_BK(kBias); break;
+      default: DGS_BK(kBiasReplace); break;
+    }
+#undef DGS_BK
+    if (smem_max > 48 * 1024)
+      DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    int per_sm = 0;
+    DGS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBkThreads, smem_max));
+    if (per_sm >= 1) {
+      if (per_sm > 4) per_sm = 4;
+      const int grid = sm_count() * per_sm;
+      GraphSrc src_copy = src;
+      BlocksWs ws_copy = ws;
+      static const bool trace = getenv("DGS_BLOCKS_TRACE") != nullptr;
+      static unsigned long long *trace_dev = nullptr;
+      if (trace && !trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(unsigned long long));
+      a.trace = trace ? trace_dev : nullptr;
+      void *params[] = {&src_copy, &ws_copy, &a};
+      DGS_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kBkThreads), params, smem_max, st));
+      dgsb::g_launches += 1;
+      if (trace) {
+        unsigned long long h[1 + 8 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(unsigned long long) * (1 + 7 * L), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[dgs coop trace us, grid %d] pick sync rank tail sync emit sync:", grid);
+        for (int i = 1; i < 1 + 7 * L; ++i)
+          fprintf(stderr, "%s%.1f", (i - 1) % 7 == 0 ? " | " : " ", (double)(h[i] - h[i - 1]) * 1e-3);
+        fprintf(stderr, "\n");
+      }
+      return 0;
+    }
+  }
+
+  // ---- multi-kernel path
   static const bool timing = getenv("DGS_BLOCKS_TIMING") != nullptr;
   cudaEvent_t evs[3 * 16 + 1];
   int nev = 0;
@@ -589,14 +862,9 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     const int k = (int)k64;
     const int64_t cur_ub = ubs[l];
     const int64_t nnz_ub = cur_ub * k64;
-    DGS_REQUIRE(cap_edges[l] >= nnz_ub, "sample_blocks: layer %d edge capacity %lld < %lld", l,
-                (long long)cap_edges[l], (long long)nnz_ub);
-    DGS_REQUIRE(cap_frontier[l] >= cur_ub + nnz_ub,
-                "sample_blocks: layer %d frontier capacity %lld < %lld", l,
-                (long long)cap_frontier[l], (long long)(cur_ub + nnz_ub));
     // Hops are numbered h = epoch L + l over the life of the workspace; hop h uses state h & 1 and
     // wipes what hop h - 1 left in the other one (for l = 0 that is the last hop of the previous
-    // call, whose live seed count the emit kernel parked in ws.pending_S; 0 after ws_init).
+    // call, whose live seed count the emit phase parked in ws.pending_S; 0 after ws_init).
     const int64_t h = epoch * L + l;
     const HopState &cur = ws.hop[h & 1];
     const HopState &prev = ws.hop[(h + 1) & 1];
@@ -606,7 +874,6 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     const long long *prev_dev = ws.pending_S;
     int64_t *nnz_dev = counts_dev + 2 * l, *nf_dev = counts_dev + 2 * l + 1;
     const uint64_t key = rng_seed + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
-    // shared memory: tile kernel = 128 k positions (+ 8 k keys when biased)
     size_t smem_tile = (size_t)kPkSeeds * k * sizeof(int);
     if (mode == kBias) smem_tile += (size_t)kBkWarps * k * sizeof(float);
     if (k > 0 && smem_tile <= 64 * 1024) {
@@ -664,7 +931,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     fused_rank_kernel<<<grid_rank, kBkThreads, 0, st>>>(cur_ub, cur_dev, k, cur, ws, nnz_dev, nf_dev);
     DGS_LAUNCH_CHECK();
     mark();
-    const int grid_emit = grid_for(cur_ub + nnz_ub, kBkThreads, 8);
+    const int grid_emit = grid_for(cur_ub + nnz_ub, kBkThreads * 2, 8);
     fused_emit_kernel<IdT><<<grid_emit, kBkThreads, 0, st>>>(
         cur_seeds, cur_ub, cur_dev, k, (const IdT *)ws.pad_col, cur, ws, (IdT *)out_frontier[l],
         (IdT *)out_row[l], (IdT *)out_col[l]);
@@ -721,7 +988,7 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
                                  void *const *out_row, void *const *out_col,
                                  const int64_t *cap_edges, const int64_t *cap_frontier,
                                  int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
-                                 void *stream) {
+                                 int64_t *counts_host, void *stream) {
   DGS_REQUIRE(g && fan_out && out_frontier && out_row && out_col && cap_edges && cap_frontier &&
                   counts_dev && ws,
               "dgs_sample_blocks: null argument");
@@ -730,6 +997,10 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
   if (num_seeds == 0) {
     DGS_REQUIRE(num_layers >= 1 && num_layers <= 16, "dgs_sample_blocks: 1..16 layers supported");
     DGS_CUDA_OK(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 2 * num_layers, st));
+    if (counts_host) {
+      memset(counts_host, 0, sizeof(int64_t) * 2 * num_layers);
+      DGS_CUDA_OK(cudaStreamSynchronize(st));
+    }
     return 0;
   }
   DGS_REQUIRE(seeds != nullptr, "dgs_sample_blocks: null seeds");
@@ -740,12 +1011,20 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
               (long long)ws_bytes, (long long)p.bytes);
   GraphSrc src;
   if (build_graph_src(g, &src)) return 1;
+  int rc = 0;
   DGS_ITYPE_SWITCH(g->itype, IdT, {
     DGS_ITYPE_SWITCH(g->etype, ET, {
-      return launch_blocks<IdT, ET>(src, (const IdT *)seeds, num_seeds, num_layers, fan_out,
-                                    replace, rng_seed, epoch, out_frontier, out_row, out_col,
-                                    cap_edges, cap_frontier, counts_dev, w, st);
+      rc = launch_blocks<IdT, ET>(src, (const IdT *)seeds, num_seeds, num_layers, fan_out, replace,
+                                  rng_seed, epoch, out_frontier, out_row, out_col, cap_edges,
+                                  cap_frontier, counts_dev, w, st);
     });
   });
+  if (rc) return rc;
+  if (counts_host) {
+    // the one host round trip of the batch: hop sizes -> (pinned) host memory
+    DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * num_layers,
+                                cudaMemcpyDeviceToHost, st));
+    DGS_CUDA_OK(cudaStreamSynchronize(st));
+  }
   return 0;
 }

@@ -183,8 +183,10 @@ class _BlockPipeline:
                 ubs.append(ub)
                 nnz_ubs.append(ub * k)
                 ub = ub + ub * k
-            total = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
-            pl = {"L": L, "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "ws": None}
+            used = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
+            total = (used + 1) & ~1   # keeps the int64 counts at the arena tail 8-byte aligned
+            pl = {"L": L, "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "pad": total - used,
+                  "ws": None}
             if total <= MAX_FUSED_ELEMS:
                 fo = _lib.i64_array(fan_out)
                 it = ID_DTYPES[self._id_dtype]
@@ -194,9 +196,19 @@ class _BlockPipeline:
                 ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
                 check(l.dgs_sample_blocks_ws_init(ptr(ws), nbytes, it, S, L, fo, stream()),
                       "sample_blocks_ws_init")
-                pl.update(ws=ws, ws_bytes=int(nbytes), fo=fo, epoch=0, cap_edges=_lib.i64_array(nnz_ubs),
+                es = torch.empty(0, dtype=self._id_dtype).element_size()
+                offs, off = [], 0
+                for u, n in zip(ubs, nnz_ubs):
+                    offs.append((off, off + u + n, off + u + 2 * n))
+                    off += u + 3 * n
+                counts_host = torch.empty(2 * L, dtype=torch.int64).pin_memory()
+                pl.update(ws=ws, ws_bytes=int(nbytes), fo=fo, epoch=0, es=es, offs=offs,
+                          cap_edges=_lib.i64_array(nnz_ubs),
                           cap_front=_lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
-                          counts_host=torch.empty(2 * L, dtype=torch.int64).pin_memory())
+                          a_fr=(C.c_void_p * L)(), a_row=(C.c_void_p * L)(),
+                          a_col=(C.c_void_p * L)(), count_slots=2 * L * 8 // es,
+                          counts_host=counts_host, counts_np=counts_host.numpy(),
+                          counts_ptr=counts_host.data_ptr())
             if len(self._plans) > 8:
                 self._plans.clear()
             self._plans[key] = pl
@@ -223,35 +235,35 @@ class _BlockPipeline:
                 # worst-case buffers would be unreasonable (huge fan-out used as "all neighbours"):
                 # size every hop exactly instead, at the price of a host sync per hop
                 return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
-            arena = torch.empty(pl["total"], dtype=seeds.dtype, device=self._device)
-            fr, rows, cols = [], [], []
-            off = 0
-            for u, n in zip(pl["ubs"], pl["nnz_ubs"]):
-                fr.append(arena[off:off + u + n]); off += u + n
-                rows.append(arena[off:off + n]); off += n
-                cols.append(arena[off:off + n]); off += n
-            es = arena.element_size()
+            # one arena per batch: [frontier | row | col] per hop, worst-case sized, + 2 L counts
+            arena = torch.empty(pl["total"] + pl["count_slots"], dtype=seeds.dtype, device=self._device)
             base = arena.data_ptr()
-            counts_dev = torch.empty(2 * L, dtype=torch.int64, device=self._device)
+            es = pl["es"]
+            a_fr, a_row, a_col = pl["a_fr"], pl["a_row"], pl["a_col"]
+            for li, (of, orow, ocol) in enumerate(pl["offs"]):
+                a_fr[li] = base + of * es
+                a_row[li] = base + orow * es
+                a_col[li] = base + ocol * es
+            counts_dev = base + pl["total"] * es
             check(l.dgs_sample_blocks(
                 C.byref(self._graph), seeds.data_ptr(), S, L, pl["fo"], int(bool(replace)),
-                C.c_uint64(rng_seed),
-                _lib.vp_array([base + t.storage_offset() * es for t in fr]),
-                _lib.vp_array([base + t.storage_offset() * es for t in rows]),
-                _lib.vp_array([base + t.storage_offset() * es for t in cols]),
-                pl["cap_edges"], pl["cap_front"], counts_dev.data_ptr(), pl["ws"].data_ptr(),
-                pl["ws_bytes"], pl["epoch"], stream()), "sample_blocks")
+                C.c_uint64(rng_seed), a_fr, a_row, a_col, pl["cap_edges"], pl["cap_front"],
+                counts_dev, pl["ws"].data_ptr(), pl["ws_bytes"], pl["epoch"], pl["counts_ptr"],
+                stream()), "sample_blocks")          # syncs once, counts land in pinned memory
             pl["epoch"] += 1
-            ch = pl["counts_host"]
-            ch.copy_(counts_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the only host sync of the batch
-            counts = ch.tolist()
+            counts = pl["counts_np"].tolist()
+            # exact-size views of the arena in one split
+            sizes = []
+            for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
+                nnz, nf = counts[2 * li], counts[2 * li + 1]
+                sizes += [nf, u + n - nf, nnz, n - nnz, nnz, n - nnz]
+            sizes.append(pl["pad"] + pl["count_slots"])
+            parts = arena.split_with_sizes(sizes)
         out = []
         cur = seeds
         for li in range(L):
-            nnz, nf = counts[2 * li], counts[2 * li + 1]
-            frontier = fr[li][:nf]
-            out.append((cur, frontier, rows[li][:nnz], cols[li][:nnz]))
+            frontier = parts[6 * li]
+            out.append((cur, frontier, parts[6 * li + 2], parts[6 * li + 4]))
             cur = frontier
         return out
 

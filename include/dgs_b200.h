@@ -177,7 +177,10 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
  * the same (itype, num_seeds, num_layers, fan_out); epoch = number of dgs_sample_blocks calls
  * already made on this workspace since its init (0, 1, 2, ...): the relabel table a call leaves
  * dirty is wiped by the first kernel of the next call, which needs to know which of the two
- * alternating tables that is.  3 kernels per hop, no memset, no trailing clean-up launch. */
+ * alternating tables that is.  One cooperative launch per batch (or 3 kernels per hop when the
+ * fan-out is too large for the tile kernels), no memset, no trailing clean-up launch.
+ * counts_host (optional, pinned host memory, 2 L int64): when non-NULL the counts are copied back
+ * and the stream is synchronised before returning - the single host round trip of a batch. */
 int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
                                    const int64_t *fan_out);
 int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
@@ -186,7 +189,7 @@ int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds
                       const int64_t *fan_out, int replace, uint64_t rng_seed,
                       void *const *out_frontier, void *const *out_row, void *const *out_col,
                       const int64_t *cap_edges, const int64_t *cap_frontier, int64_t *counts_dev,
-                      void *ws, int64_t ws_bytes, int64_t epoch, void *stream);
+                      void *ws, int64_t ws_bytes, int64_t epoch, int64_t *counts_host, void *stream);
 
 /* ------------------------------------------------------------------ relabel
  * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):

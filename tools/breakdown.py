@@ -66,7 +66,7 @@ def main():
     def raw(i):
         _lib.check(l.dgs_sample_blocks(C.byref(pipe._graph), seeds[i].data_ptr(), S, L, pl["fo"], 0,
                                        C.c_uint64(i + 1), a_fr, a_r, a_c, pl["cap_edges"], pl["cap_front"],
-                                       counts_dev.data_ptr(), pl["ws"].data_ptr(), pl["ws_bytes"], pl["epoch"], stream()))
+                                       counts_dev.data_ptr(), pl["ws"].data_ptr(), pl["ws_bytes"], pl["epoch"], None, stream()))
         pl["epoch"] += 1
 
     raw(0)
