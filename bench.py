@@ -283,28 +283,28 @@ def run_b200(args, fan_out):
     for i in range(2):   # set-up (allocator pools, lazily enabled peer mappings) - not a timed step
         step_device(i)
         step_e2e(i)
-    for i in range(W):
-        step_device(i)
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for i in range(W):
+        step_device(i)
+    barrier()
     launches0 = dgs.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    edges = rows = 0
+    edges = rows = hop_seeds = 0
     frontiers = []
     e0.record()
     for i in range(W, W + K):
         blocks, x = step_device(i)
         edges += sum(b[2].numel() for b in blocks)
+        hop_seeds += sum(b[0].numel() for b in blocks)
         rows += x.shape[0]
         frontiers.append(blocks[-1][1])
     e1.record()
     barrier()
     launches = dgs.launch_count() - launches0
     ms = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop() if rank == 0 else None
     total_edges = sum_over_ranks(edges)
     total_rows = sum_over_ranks(rows)
     # ---- roofline of the dominant kernel (the extract gather): the K launches of the timed region
@@ -325,6 +325,17 @@ def run_b200(args, fan_out):
     ex_ms = x0.elapsed_time(x1)
     ex_bytes = sum(f.numel() * (2 * row_bytes + 8) for f in frontiers)
     del outs
+    # same for the sampling kernel (one cooperative launch per batch): K batches back to back
+    pipe = sampler._pipe
+    keep = [pipe.enqueue_only(seeds_dev[i], fan_out) for i in range(min(3, K))]
+    barrier()
+    x0.record()
+    keep = [pipe.enqueue_only(seeds_dev[W + i], fan_out, rng_seed=i + 1) for i in range(K)]
+    x1.record()
+    torch.cuda.synchronize()
+    sm_ms = x0.elapsed_time(x1)
+    del keep
+    sm_bytes = 24.0 * (hop_seeds + edges)   # 24 * (S + nnz) per hop
 
     # ---- end-to-end timing through the plugin API with host seeds / host result ("e2e")
     for i in range(W):
@@ -339,6 +350,7 @@ def run_b200(args, fan_out):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_edges = sum_over_ranks(t_edges)
+    clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through both timed regions
 
     if rank != 0:
         if world > 1:
@@ -346,7 +358,33 @@ def run_b200(args, fan_out):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    achieved = ex_bytes / (ex_ms * 1e-3) / 1e9
+    ex_gbs = ex_bytes / (ex_ms * 1e-3) / 1e9
+    sm_gbs = sm_bytes / (sm_ms * 1e-3) / 1e9
+    traffic = {}
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
+        for name, key in (("gather_rows", "extract"), ("fused_batch", "sample")):
+            d = prof[name][0]
+            traffic[key] = (float(d["dram__bytes_read.sum"].split()[0]) +
+                            float(d["dram__bytes_write.sum"].split()[0])) * 1e6
+    except Exception:
+        pass
+    roof_extract = {"bound": "hbm", "kernel": "gather_rows_kernel (feature extract)",
+                    "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak,
+                    "peak_source": peak_src, "traffic": traffic.get("extract"),
+                    "algorithmic_bytes": "rows * (2 * row_bytes + 8)", "avg_launch_ms": ex_ms / K,
+                    "rows_per_launch": rows / K}
+    roof_sample = {"bound": "hbm", "kernel": "fused_batch_kernel (all hops: sample + relabel, one "
+                                             "cooperative launch per batch)",
+                   "achieved": sm_gbs, "peak": peak, "unit": "GB/s", "frac": sm_gbs / peak,
+                   "peak_source": peak_src, "traffic": traffic.get("sample"),
+                   "algorithmic_bytes": "24 * (seeds + sampled edges) summed over hops",
+                   "avg_launch_ms": sm_ms / K,
+                   "note": "latency-bound at batch %d: dependent load / atomic chains and 9 grid "
+                           "barriers, not bandwidth (DESIGN.md section 5)" % args.batch}
+    dominant, other = (roof_sample, roof_extract) if sm_ms >= ex_ms else (roof_extract, roof_sample)
+    dominant = dict(dominant)
+    dominant["share_of_gpu_time"] = max(sm_ms, ex_ms) / (sm_ms + ex_ms)
     line = {
         "metric": METRIC, "value": total_edges / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -360,15 +398,12 @@ def run_b200(args, fan_out):
         "clocks": clk,
         "e2e": {"value": e2e_edges / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": args.batch * 8, "d2h_bytes_per_step": args.batch * 8 + 48,
-                "ms_per_step": ms_e2e / K,
+                "ms_per_step": ms_e2e / K, "batches_per_sec": world * K / (ms_e2e * 1e-3),
                 "note": "seeds from pinned host memory, blocks + features stay on the device (the "
                         "plugin API returns CUDA tensors), labels of the batch + hop sizes read back"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "gather_rows (feature extract)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
-                     "algorithmic_bytes": "rows * (2 * row_bytes + 8)",
-                     "avg_launch_ms": ex_ms / K, "rows_per_launch": rows / K},
+        "roofline": dominant,
+        "roofline_other": other,
     }
     if host_graph is not None:
         cb = cpu_baseline(args, fan_out, host_graph, args.cpu_baseline_seconds)

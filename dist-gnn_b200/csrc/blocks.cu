@@ -280,6 +280,14 @@ constexpr int kPkSeeds = 128;  // seeds per pick tile
 constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick / emit phases
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
 
+// Seeds per pick tile: up to 128, fewer when the hop is small so that every CTA of the grid gets
+// a tile (the phases are latency chains - more CTAs in flight, not longer chains per CTA).
+__device__ __forceinline__ int pick_tile_seeds(int64_t S) {
+  int64_t per = (S + gridDim.x - 1) / gridDim.x;
+  per = (per + 7) & ~7ll;
+  return (int)max((int64_t)8, min((int64_t)kPkSeeds, per));
+}
+
 template <typename T>
 __device__ __forceinline__ T ldcg(const T *p) {
   return __ldcg(p);
@@ -320,11 +328,12 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
   unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
   float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tiles = (S + kPkSeeds - 1) / kPkSeeds;
+  const int ts = pick_tile_seeds(S);
+  const int64_t tiles = (S + ts - 1) / ts;
   const bool with_replace = (MODE == kUniformReplace || MODE == kBiasReplace);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t i0 = tile * kPkSeeds;
-    const int ns = (int)min((int64_t)kPkSeeds, S - i0);
+    const int64_t i0 = tile * ts;
+    const int ns = (int)min((int64_t)ts, S - i0);
     __syncthreads();  // previous tile's readers are done with the shared arrays
     long long seed_nid = 0;
     uint64_t seed_pos = 0;
@@ -637,7 +646,7 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
   const long long pS_live = *prev_S_dev;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
   pick_tile_phase<IdT, ET, MODE>(g, seeds, S_ub, S, k, rng_key, pad_col, cur, cap_mask);
-  wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + kPkSeeds - 1) / kPkSeeds);
+  wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S));
 }
 
 __global__ void __launch_bounds__(kBkThreads)
@@ -710,7 +719,7 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
                                    (IdT *)ws.pad_col, cur, a.cap_mask);
-    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + kPkSeeds - 1) / kPkSeeds);
+    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S));
     stamp();
     grid.sync();
     stamp();
@@ -877,7 +886,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     size_t smem_tile = (size_t)kPkSeeds * k * sizeof(int);
     if (mode == kBias) smem_tile += (size_t)kBkWarps * k * sizeof(float);
     if (k > 0 && smem_tile <= 64 * 1024) {
-      const int grid = std::max(grid_for(cur_ub, kPkSeeds, 4),
+      const int grid = std::max(grid_for(cur_ub, 8, 2),  // tiles shrink to 8 seeds on small hops
                                 grid_for(prev_ub * (1 + (int64_t)prev_k), kBkThreads * 4, 4));
 #define DGS_TPICK(M)                                                                            \
   do {                                                                                          \

@@ -26,10 +26,15 @@ struct RowSource {
   const LocSlot *loc;
   uint64_t cap_mask;
   PtrTable shards;
+  int mod_world;  // > 0: row n lives in shard n % mod_world at slot n / mod_world (no table)
 };
 
 template <typename IdT>
 __device__ __forceinline__ const char *resolve_row(const RowSource &src, IdT nid, int64_t row_bytes) {
+  if (src.mod_world > 0) {
+    const long long n = (long long)nid;
+    return (const char *)src.shards.p[n % src.mod_world] + (n / src.mod_world) * row_bytes;
+  }
   if (src.loc != nullptr) {
     long long v = loc_lookup(src.loc, src.cap_mask, (long long)nid);
     if (v >= 0) {
@@ -328,6 +333,29 @@ extern "C" int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_ta
   src.loc = (const LocSlot *)loc_table;
   src.cap_mask = (uint64_t)capacity - 1;
   bool al = aligned16(out) && (host_table == nullptr || aligned16(host_table));
+  for (int d = 0; d < feat->world; ++d) {
+    src.shards.p[d] = feat->ptrs[d];
+    al = al && aligned16(feat->ptrs[d]);
+  }
+  DGS_ITYPE_SWITCH(itype, IdT, {
+    return launch_gather<IdT>(src, (const IdT *)nids, n, row_bytes, (char *)out, algo, al,
+                              (cudaStream_t)stream);
+  });
+  return 0;
+}
+
+// Modulo-sharded gather: every row is cached, row n lives in shard n % world at slot n / world
+// (the layout of the synthetic multi-GPU benchmarks) - the owner is arithmetic, so the
+// location table and its random 16-byte probe per row disappear.
+extern "C" int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_bytes, int itype,
+                                   const void *nids, int64_t n, void *out, int algo, void *stream) {
+  DGS_REQUIRE(n >= 0 && row_bytes > 0, "dgs_extract_sharded: bad sizes");
+  if (n == 0) return 0;
+  DGS_REQUIRE(feat && nids && out, "dgs_extract_sharded: null pointer");
+  RowSource src;
+  memset(&src, 0, sizeof(src));
+  src.mod_world = feat->world;
+  bool al = aligned16(out);
   for (int d = 0; d < feat->world; ++d) {
     src.shards.p[d] = feat->ptrs[d];
     al = al && aligned16(feat->ptrs[d]);

@@ -248,17 +248,21 @@ int build_graph_src(const dgs_graph_t *g, GraphSrc *out) {
   out->indices = g->indices;
   out->probs = g->probs;
   if (g->p2p_indptr) {
-    DGS_REQUIRE(g->p2p_indices && g->loc_table, "graph: cached source needs indptr, indices and "
-                "a location table");
-    DGS_REQUIRE(g->loc_capacity > 0 && (g->loc_capacity & (g->loc_capacity - 1)) == 0,
+    DGS_REQUIRE(g->p2p_indices && (g->loc_table || g->loc_mod_world > 0),
+                "graph: cached source needs indptr, indices and a location table (or modulo sharding)");
+    DGS_REQUIRE(g->loc_mod_world > 0 ||
+                    (g->loc_capacity > 0 && (g->loc_capacity & (g->loc_capacity - 1)) == 0),
                 "graph: location-table capacity must be a power of two");
+    DGS_REQUIRE(g->loc_mod_world == 0 || g->loc_mod_world == g->p2p_indptr->world,
+                "graph: loc_mod_world must equal the p2p world size");
+    out->mod_world = g->loc_mod_world;
     for (int d = 0; d < g->p2p_indptr->world; ++d) {
       out->sh_indptr.p[d] = g->p2p_indptr->ptrs[d];
       out->sh_indices.p[d] = g->p2p_indices->ptrs[d];
       if (g->p2p_probs) out->sh_probs.p[d] = g->p2p_probs->ptrs[d];
     }
-    out->loc = (const LocSlot *)g->loc_table;
-    out->cap_mask = (uint64_t)g->loc_capacity - 1;
+    out->loc = g->loc_mod_world > 0 ? nullptr : (const LocSlot *)g->loc_table;
+    out->cap_mask = g->loc_mod_world > 0 ? 0 : (uint64_t)g->loc_capacity - 1;
   } else {
     DGS_REQUIRE(g->indptr && g->indices, "graph: null indptr / indices");
   }

@@ -12,6 +12,7 @@ struct GraphSrc {
   PtrTable sh_indptr, sh_indices, sh_probs;
   const LocSlot *loc;
   uint64_t cap_mask;
+  int mod_world;  // > 0: every node is cached, node n lives on device n % mod_world at slot n / mod_world
 };
 
 enum PickMode { kUniform = 0, kUniformReplace = 1, kBias = 2, kBiasReplace = 3 };
@@ -37,7 +38,10 @@ template <typename ET>
 __device__ __forceinline__ void resolve_seed(const GraphSrc &g, long long nid, int *dev,
                                              long long *begin, long long *deg) {
   long long v = -1;
-  if (g.loc != nullptr) v = loc_lookup(g.loc, g.cap_mask, nid);
+  if (g.mod_world > 0)
+    v = ((nid % g.mod_world) << kDevShift) | (nid / g.mod_world);  // arithmetic owner, no table
+  else if (g.loc != nullptr)
+    v = loc_lookup(g.loc, g.cap_mask, nid);
   long long b, e;
   if (v >= 0) {
     *dev = (int)((v >> kDevShift) & 0xff);
@@ -138,65 +142,160 @@ __device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
       emit_picks<IdT, Emit, kPos>(row, w_idx, k, lane, emit);
     }
   } else if (MODE == kBias) {
-    // fill the reservoir with the first k items
-    for (int t = lane; t < k; t += 32) {
-      const float w = wrow[t];
-      const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
-      w_key[t] = w > 0.f ? __log2f(u) / w : -INFINITY;
-      w_idx[t] = t;
-    }
-    __syncwarp();
-    // (min key, its slot) over the reservoir
-    float lmin = INFINITY;
-    int lslot = -1;
-    for (int c = lane; c < k; c += 32) {
-      const float v = w_key[c];
-      if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
-    }
-    float wmin = lmin;
-    int wslot = lslot;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-      const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-      if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
-    }
-    for (int t0 = k; t0 < deg; t0 += 32) {
-      const int t = t0 + lane;
-      float key = -INFINITY;
-      if (t < deg) {
-        const float w = wrow[t];
-        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
-        key = w > 0.f ? __log2f(u) / w : -INFINITY;
+    if (k <= 32) {
+      // reservoir of the k largest keys held one slot per lane in REGISTERS: an insertion is a
+      // broadcast + a 5-step arg-min butterfly, no shared-memory traffic
+      float rkey = INFINITY;   // lanes >= k never hold the minimum
+      int ridx = 0;
+      if (lane < k) {
+        const float w = wrow[lane];
+        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)lane));
+        rkey = w > 0.f ? __log2f(u) / w : -INFINITY;
+        ridx = lane;
       }
-      unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
-      while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float ck = __shfl_sync(0xffffffffu, key, src);
-        const int ci = t0 + src;
-        if (ck > wmin) {  // warp-uniform
-          if (lane == 0) { w_key[wslot] = ck; w_idx[wslot] = ci; }
-          __syncwarp();
-          lmin = INFINITY;
-          lslot = -1;
-          for (int c = lane; c < k; c += 32) {
-            const float v = w_key[c];
-            if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
-          }
-          wmin = lmin;
-          wslot = lslot;
+      float wmin = rkey;
+      int wslot = lane;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-            const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-            if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+        const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+        if (ov < wmin || (ov == wmin && os < wslot)) { wmin = ov; wslot = os; }
+      }
+      for (int t0 = k & ~3; t0 < deg; t0 += 512) {
+        float w4[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tb = t0 + 128 * q + 4 * lane;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int t = tb + c;
+            w4[q][c] = (t >= k && t < deg) ? wrow[t] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tq = t0 + 128 * q;
+          if (tq >= deg) break;  // warp-uniform
+          const int tb = tq + 4 * lane;
+          float key4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (tb < deg) {
+            const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
+            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (w4[q][c] > 0.f) key4[c] = __log2f(u32_to_unit(rr[c])) / w4[q][c];
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float key = key4[c];
+            unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float ck = __shfl_sync(0xffffffffu, key, src);
+              if (ck > wmin) {  // warp-uniform
+                if (lane == wslot) { rkey = ck; ridx = tq + 4 * src + c; }
+                wmin = rkey;
+                wslot = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+                  const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+                  if (ov < wmin || (ov == wmin && os < wslot)) { wmin = ov; wslot = os; }
+                }
+              }
+            }
           }
         }
       }
+      if (lane < k) emit(lane, pick_value<IdT, kPos>(row, ridx));
+    } else {
+      // fill the reservoir with the first k items
+      for (int t = lane; t < k; t += 32) {
+        const float w = wrow[t];
+        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
+        w_key[t] = w > 0.f ? __log2f(u) / w : -INFINITY;
+        w_idx[t] = t;
+      }
+      __syncwarp();
+      // (min key, its slot) over the reservoir
+      float lmin = INFINITY;
+      int lslot = -1;
+      for (int c = lane; c < k; c += 32) {
+        const float v = w_key[c];
+        if (v < lmin || lslot < 0) { lmin = v; lslot = c; }
+      }
+      float wmin = lmin;
+      int wslot = lslot;
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+        const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+        if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
+      }
+      // stream the rest of the row, 512 weights per warp pass: every lane owns 4 quads of 4
+      // consecutive elements (quad q = elements t0 + 128 q + 4 lane ..+3 = exactly one Philox block:
+      // draw t is component t & 3 of block t >> 2, the same mapping as philox_u32, so the sample
+      // does not depend on this blocking).  All 16 weight loads of a lane are issued before any is
+      // used - a hub row (deg ~ 10^4) is a chain of ~deg/512 memory round trips instead of deg/32.
+      for (int t0 = k & ~3; t0 < deg; t0 += 512) {
+        float w4[4][4];
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tb = t0 + 128 * q + 4 * lane;
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int t = tb + c;
+            w4[q][c] = (t >= k && t < deg) ? wrow[t] : 0.f;
+          }
+        }
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tq = t0 + 128 * q;
+          if (tq >= deg) break;  // warp-uniform
+          const int tb = tq + 4 * lane;
+          float key4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (tb < deg) {
+            const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
+            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+  #pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (w4[q][c] > 0.f) key4[c] = __log2f(u32_to_unit(rr[c])) / w4[q][c];
+          }
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float key = key4[c];
+            unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float ck = __shfl_sync(0xffffffffu, key, src);
+              const int ci = tq + 4 * src + c;
+              if (ck > wmin) {  // warp-uniform
+                if (lane == 0) { w_key[wslot] = ck; w_idx[wslot] = ci; }
+                __syncwarp();
+                lmin = INFINITY;
+                lslot = -1;
+                for (int z = lane; z < k; z += 32) {
+                  const float v = w_key[z];
+                  if (v < lmin || lslot < 0) { lmin = v; lslot = z; }
+                }
+                wmin = lmin;
+                wslot = lslot;
+  #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
+                  const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
+                  if (os >= 0 && (wslot < 0 || ov < wmin || (ov == wmin && os < wslot))) { wmin = ov; wslot = os; }
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      emit_picks<IdT, Emit, kPos>(row, w_idx, k, lane, emit);
     }
-    __syncwarp();
-    emit_picks<IdT, Emit, kPos>(row, w_idx, k, lane, emit);
   } else {  // kBiasReplace
     // pass 1: total weight, with exactly the arithmetic of pass 2
     float total = 0.f;

@@ -29,6 +29,7 @@ class Graph(C.Structure):
         ("p2p_probs", c_vp),
         ("loc_table", c_vp),
         ("loc_capacity", c_i64),
+        ("loc_mod_world", C.c_int32),
     ]
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "dgs_index_select": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "dgs_extract_p2p": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp,
                                   C.c_int, c_vp]),
+    "dgs_extract_sharded": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "dgs_extract_indptr_ws_bytes": (c_i64, [c_i64]),
     "dgs_extract_indptr": (C.c_int, [C.c_int, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dgs_extract_edge_data": (C.c_int, [C.c_int, C.c_int, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp,

@@ -113,10 +113,35 @@ class TensorP2PServer:
             pass
 
 
-def _build_loc_table(local_nids, num_nodes, device):
+def _is_modulo_sharded(local_nids, num_nodes):
+    """True on every rank iff rank r caches exactly [r, r + P, r + 2 P, ...] in that order, i.e.
+    node n lives on GPU n % P at shard slot n // P.  Collective (one int64 all-gather)."""
+    l = lib()
+    world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
+    want = (num_nodes - rank + world - 1) // world
+    mine = 0
+    if local_nids.numel() == want:
+        exp = torch.arange(rank, num_nodes, world, dtype=local_nids.dtype, device=local_nids.device)
+        mine = int(torch.equal(local_nids, exp))
+    flags = (C.c_int64 * world)()
+    check(l.dgs_nccl_allgather_i64(mine, flags), "modulo-sharding check")
+    return all(int(f) == 1 for f in flags)
+
+
+def _build_loc_table(local_nids, num_nodes, device, allow_modulo=True):
     """All-gather the per-rank cached id lists and build the packed location table
     (CreateNidsP2PCacheHashMapCUDA, src/hashmap/cuda/hashmap.cu:15-77).  Returns
-    (table int64[2*cap], capacity, n_unique, per-rank id lists)."""
+    (table int64[2*cap] or None, capacity, n_unique, mod_world).  When the cache sets are an exact
+    modulo sharding of all nodes the owner is arithmetic: no table is built (mod_world = P)."""
+    l = lib()
+    world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
+    if allow_modulo and _is_modulo_sharded(local_nids, num_nodes):
+        return None, l.dgs_loc_table_capacity(num_nodes), num_nodes, world
+    table, cap, n_unique = _hash_loc_table(local_nids, num_nodes, device)
+    return table, cap, n_unique, 0
+
+
+def _hash_loc_table(local_nids, num_nodes, device):
     l = lib()
     world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
     lists = ops._allgather_tensors(local_nids)
@@ -135,7 +160,7 @@ def _build_loc_table(local_nids, num_nodes, device):
                                 _lib.vp_array([ptr(t) for t in lists]),
                                 _lib.i64_array([t.numel() for t in lists]), stream()),
           "location table build")
-    return table, cap, n_unique, lists
+    return table, cap, n_unique
 
 
 def _unpack_loc_table(table, cap, dtype):
@@ -267,6 +292,32 @@ class _BlockPipeline:
             cur = frontier
         return out
 
+    def enqueue_only(self, seeds, fan_out, replace=False, rng_seed=1):
+        """Extension (bench.py's roofline leg): enqueue one batch WITHOUT the host round trip and
+        return the raw arena (worst-case sized, counts in its last 2 L int64).  Lets K batches be
+        issued back to back so the kernel's own duration can be timed with CUDA events."""
+        l = lib()
+        fan_out = [int(k) for k in fan_out]
+        L = len(fan_out)
+        S = seeds.numel()
+        pl = self._plan(S, fan_out)
+        if pl["ws"] is None:
+            raise RuntimeError("enqueue_only needs the fused path")
+        with torch.cuda.device(self._device):
+            arena = torch.empty(pl["total"] + pl["count_slots"], dtype=seeds.dtype, device=self._device)
+            base, es = arena.data_ptr(), pl["es"]
+            for li, (of, orow, ocol) in enumerate(pl["offs"]):
+                pl["a_fr"][li] = base + of * es
+                pl["a_row"][li] = base + orow * es
+                pl["a_col"][li] = base + ocol * es
+            check(l.dgs_sample_blocks(
+                C.byref(self._graph), seeds.data_ptr(), S, L, pl["fo"], int(bool(replace)),
+                C.c_uint64(rng_seed), pl["a_fr"], pl["a_row"], pl["a_col"], pl["cap_edges"],
+                pl["cap_front"], base + pl["total"] * es, pl["ws"].data_ptr(), pl["ws_bytes"],
+                pl["epoch"], None, stream()), "sample_blocks")
+            pl["epoch"] += 1
+        return arena
+
     def _sample_per_hop(self, seeds, fan_out, replace, rng_seed):
         """Host-synchronised hop loop (used for fan-out -1 = all neighbours, an extension)."""
         out = []
@@ -333,37 +384,72 @@ class P2PCacheSampler:
             if nids.dtype != indices.dtype:
                 nids = nids.to(indices.dtype)
             sub_indptr = ops._Test_ExtractIndptr(nids, indptr)
-            self.gpu_indptr_ = TensorP2PServer(sub_indptr)
             sub_indices = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, indices)
+            sub_probs = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, probs) if self.bias_ else None
+            self._adopt_shards(sub_indptr, sub_indices, sub_probs, nids, num_nodes)
+
+    def _adopt_shards(self, sub_indptr, sub_indices, sub_probs, nids, num_nodes):
+        """Publish the local sub-CSR as p2p shards, build the location map, make the graph handle."""
+        indptr, indices, probs = self.cpu_indptr_, self.cpu_indices_, self.cpu_probs_
+        with torch.cuda.device(self._device):
+            self.gpu_indptr_ = TensorP2PServer(sub_indptr)
             # a cached set without edges still needs a non-empty shard for IPC
             self.gpu_indices_ = TensorP2PServer(
-                sub_indices if sub_indices.numel() else torch.zeros(1, dtype=indices.dtype,
+                sub_indices if sub_indices.numel() else torch.zeros(1, dtype=sub_indices.dtype,
                                                                     device=self._device))
             self._num_cached_edges = sub_indices.numel()
             self.gpu_probs_ = None
             if self.bias_:
-                sub_probs = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, probs)
                 self.gpu_probs_ = TensorP2PServer(
-                    sub_probs if sub_probs.numel() else torch.zeros(1, dtype=probs.dtype,
+                    sub_probs if sub_probs.numel() else torch.zeros(1, dtype=torch.float32,
                                                                     device=self._device))
-            self._table, self._cap, self._n_unique, _ = _build_loc_table(nids, num_nodes,
-                                                                         self._device)
+            self._nids = nids
+            self._num_nodes = num_nodes
+            self._table, self._cap, self._n_unique, self._mod_world = _build_loc_table(
+                nids, num_nodes, self._device)
             torch.cuda.current_stream().synchronize()
             _barrier()
         all_cached = self._n_unique >= num_nodes
         g = _lib.Graph()
-        g.itype = itype(indices, "indices")
-        g.etype = itype(indptr, "indptr")
+        g.itype = itype(sub_indices, "indices")
+        g.etype = itype(sub_indptr, "indptr")
         g.indptr = _host_source(indptr, "indptr", all_cached)
         g.indices = _host_source(indices, "indices", all_cached)
         g.probs = _host_source(probs, "probs", all_cached) if self.bias_ else None
         g.p2p_indptr = self.gpu_indptr_._handle
         g.p2p_indices = self.gpu_indices_._handle
         g.p2p_probs = self.gpu_probs_._handle if self.bias_ else None
-        g.loc_table = ptr(self._table)
+        g.loc_table = ptr(self._table) if self._table is not None else None
         g.loc_capacity = self._cap
+        g.loc_mod_world = self._mod_world
         self._graph = g
-        self._pipe = _BlockPipeline(g, self._device, indices.dtype)
+        self._pipe = _BlockPipeline(g, self._device, sub_indices.dtype)
+
+    @classmethod
+    def from_device_shards(cls, sub_indptr, sub_indices, sub_probs, cache_nids, num_nodes,
+                           device_id, cpu_indptr=None, cpu_indices=None, cpu_probs=None):
+        """Extension: build the sampler from a sub-CSR that already lives on this GPU
+        (e.g. generated or loaded per shard) instead of extracting it from whole-graph pinned CPU
+        tensors - at papers100M / friendster scale the reference's constructor would need the full
+        graph in every process.  The cpu_* tensors are only needed when some nodes are not cached
+        on any GPU.  Collective like the normal constructor."""
+        self = cls.__new__(cls)
+        l = lib()
+        if device_id != l.dgs_nccl_rank():
+            raise RuntimeError(f"device_id ({device_id}) must equal the NCCL rank ({l.dgs_nccl_rank()})")
+        for t_, n_ in ((sub_indptr, "sub_indptr"), (sub_indices, "sub_indices"), (cache_nids, "cache_nids")):
+            check_cuda(t_, n_)
+        if cache_nids.numel() == 0 or sub_indptr.numel() != cache_nids.numel() + 1:
+            raise RuntimeError("sub_indptr must have len(cache_nids) + 1 entries, cache_nids non-empty")
+        self.device_id_ = int(device_id)
+        self._device = torch.device("cuda", self.device_id_)
+        self.bias_ = sub_probs is not None and sub_probs.numel() > 0
+        self.cpu_indptr_, self.cpu_indices_ = cpu_indptr, cpu_indices
+        self.cpu_probs_ = cpu_probs if self.bias_ else None
+        self._adopt_shards(sub_indptr.contiguous(), sub_indices.contiguous(),
+                           sub_probs.contiguous() if self.bias_ else None,
+                           cache_nids.contiguous().to(sub_indices.dtype), int(num_nodes))
+        return self
 
     def _CAPI_sample_node_classifiction(self, seeds, fan_out, replace=False, rng_seed=None):
         """NodeClassifictionSample (sampler.cc:146-166): list over hops, seed-side hop first, of
@@ -388,7 +474,9 @@ class P2PCacheSampler:
         packed table; the slot layout is implementation-defined (it is race-dependent in the
         reference as well), only lookups are comparable."""
         with torch.cuda.device(self._device):
-            return _unpack_loc_table(self._table, self._cap, self.cpu_indices_.dtype)
+            if self._table is None:   # modulo-sharded fast path: build the reference-visible table on demand
+                self._table, self._cap, _ = _hash_loc_table(self._nids, self._num_nodes, self._device)
+            return _unpack_loc_table(self._table, self._cap, self._nids.dtype)
 
     def close(self, barrier=True):
         for s in (self.gpu_indptr_, self.gpu_indices_, self.gpu_probs_):
@@ -412,33 +500,64 @@ class P2PCacheFeatureServer:
         self.device_id_ = int(device_id)
         self._device = torch.device("cuda", self.device_id_)
         self.cpu_features_ = data
-        num_items = data.shape[0]
-        stride = 1
-        for d in data.shape[1:]:
-            stride *= d
-        self._stride = stride
-        self._row_bytes = stride * data.element_size()
         with torch.cuda.device(self._device):
             nids = cache_nids.to(self._device).contiguous()
             shape = (nids.numel(),) + tuple(data.shape[1:])
             if data.is_pinned():
                 # gather the cached rows straight from pinned host memory into the shard
                 # (the reference index_selects on the CPU, then copies, feature_server.cc:33-35)
-                self.gpu_features_ = TensorP2PServer._empty(shape, data.dtype, self._device)
-                local = self.gpu_features_._CAPI_get_local_device_tensor()
-                check(l.dgs_index_select(ptr(data), self._row_bytes, itype(nids, "cache_nids"),
-                                         ptr(nids), nids.numel(), ptr(local), 1, stream()),
-                      "feature shard build")
+                server = TensorP2PServer._empty(shape, data.dtype, self._device)
+                local = server._CAPI_get_local_device_tensor()
+                stride = 1
+                for d in data.shape[1:]:
+                    stride *= d
+                check(l.dgs_index_select(ptr(data), stride * data.element_size(),
+                                         itype(nids, "cache_nids"), ptr(nids), nids.numel(),
+                                         ptr(local), 1, stream()), "feature shard build")
                 torch.cuda.current_stream().synchronize()
             else:
                 sub = data.index_select(0, cache_nids.cpu().long()).to(self._device)
-                self.gpu_features_ = TensorP2PServer(sub)
-            self._table, self._cap, self._n_unique, _ = _build_loc_table(nids, num_items,
-                                                                         self._device)
+                server = TensorP2PServer(sub)
+            self._adopt(server, nids, data.shape[0], tuple(data.shape[1:]), data.dtype)
+
+    def _adopt(self, server, nids, num_items, tail_shape, dtype):
+        self.gpu_features_ = server
+        stride = 1
+        for d in tail_shape:
+            stride *= d
+        self._stride = stride
+        self._dtype = dtype
+        self._row_bytes = stride * torch.empty(0, dtype=dtype).element_size()
+        self._nids = nids
+        self._num_items = num_items
+        with torch.cuda.device(self._device):
+            self._table, self._cap, self._n_unique, self._mod_world = _build_loc_table(
+                nids, num_items, self._device)
             torch.cuda.current_stream().synchronize()
             _barrier()
-        self._host_ptr = _host_source(data, "data", self._n_unique >= num_items)
-        self._itype_dtype = nids.dtype
+        self._host_ptr = _host_source(self.cpu_features_, "data", self._n_unique >= num_items)
+
+    @classmethod
+    def from_device_shard(cls, local_rows, cache_nids, num_items, device_id, cpu_data=None):
+        """Extension: adopt feature rows that already live on this GPU
+        (`local_rows[i]` = row of node `cache_nids[i]`); `cpu_data` (pinned) is only needed when some
+        rows are cached nowhere.  Collective like the normal constructor."""
+        self = cls.__new__(cls)
+        l = lib()
+        if device_id != l.dgs_nccl_rank():
+            raise RuntimeError(f"device_id ({device_id}) must equal the NCCL rank ({l.dgs_nccl_rank()})")
+        check_cuda(local_rows, "local_rows")
+        check_cuda(cache_nids, "cache_nids")
+        if local_rows.shape[0] != cache_nids.numel() or cache_nids.numel() == 0:
+            raise RuntimeError("local_rows must hold one row per cached id (and at least one)")
+        self.device_id_ = int(device_id)
+        self._device = torch.device("cuda", self.device_id_)
+        self.cpu_features_ = cpu_data
+        with torch.cuda.device(self._device):
+            server = TensorP2PServer(local_rows)
+        self._adopt(server, cache_nids.contiguous(), int(num_items), tuple(local_rows.shape[1:]),
+                    local_rows.dtype)
+        return self
 
     def _CAPI_get_cpu_feature(self):
         return self.cpu_features_
@@ -451,18 +570,25 @@ class P2PCacheFeatureServer:
         check_cuda(nids, "nids")
         nids = nids.contiguous()
         n = nids.numel()
-        out = torch.empty((n, self._stride), dtype=self.cpu_features_.dtype, device=nids.device)
+        out = torch.empty((n, self._stride), dtype=self._dtype, device=nids.device)
         if n:
-            check(lib().dgs_extract_p2p(self.gpu_features_._handle, self._host_ptr,
-                                        self._row_bytes, ptr(self._table), self._cap,
-                                        itype(nids, "nids"), ptr(nids), n, ptr(out), int(algo),
-                                        stream()), "_CAPI_get_feature")
+            if self._mod_world > 0:
+                check(lib().dgs_extract_sharded(self.gpu_features_._handle, self._row_bytes,
+                                                itype(nids, "nids"), ptr(nids), n, ptr(out),
+                                                int(algo), stream()), "_CAPI_get_feature")
+            else:
+                check(lib().dgs_extract_p2p(self.gpu_features_._handle, self._host_ptr,
+                                            self._row_bytes, ptr(self._table), self._cap,
+                                            itype(nids, "nids"), ptr(nids), n, ptr(out), int(algo),
+                                            stream()), "_CAPI_get_feature")
         return out
 
     def _CAPI_get_local_cache_hashmap_tensors(self):
         """Extension (tests): the (key, idx, devid) view of the location table."""
         with torch.cuda.device(self._device):
-            return _unpack_loc_table(self._table, self._cap, self._itype_dtype)
+            if self._table is None:
+                self._table, self._cap, _ = _hash_loc_table(self._nids, self._num_items, self._device)
+            return _unpack_loc_table(self._table, self._cap, self._nids.dtype)
 
     def close(self, barrier=True):
         self.gpu_features_.close(barrier)

@@ -115,6 +115,40 @@ def make_csr(num_nodes, target_edges, seed=0, device="cpu", id_dtype=torch.int64
     return indptr, indices, probs
 
 
+def make_shard(num_nodes, target_edges, rank, world, seed=0, device="cpu", id_dtype=torch.int64,
+               weights=False, node_chunk=1 << 21, classes=13):
+    """The CSR rows of the nodes GPU `rank` owns under modulo sharding (n % world == rank), generated
+    directly on `device`: (nids, sub_indptr int64[C+1], sub_indices id_dtype[sum deg], sub_probs or
+    None).  Bit-identical to slicing make_csr()'s output, without ever materialising the full edge
+    list (the global indptr - 8 bytes per node - is the only whole-graph array built)."""
+    deg = degrees(num_nodes, target_edges, seed, classes=classes, device=device)
+    gptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=gptr[1:])
+    nids = torch.arange(rank, num_nodes, world, dtype=torch.int64, device=device)
+    d = deg[nids]
+    del deg
+    sub_indptr = torch.zeros(nids.numel() + 1, dtype=torch.int64, device=device)
+    torch.cumsum(d, 0, out=sub_indptr[1:])
+    starts = gptr[nids]
+    del gptr
+    total = int(sub_indptr[-1].item())
+    sub_indices = torch.empty(total, dtype=id_dtype, device=device)
+    sub_probs = torch.empty(total, dtype=torch.float32, device=device) if weights else None
+    for a in range(0, nids.numel(), node_chunk):
+        b = min(nids.numel(), a + node_chunk)
+        lo, hi = int(sub_indptr[a].item()), int(sub_indptr[b].item())
+        if hi == lo:
+            continue
+        # global edge id of every local edge in [lo, hi)
+        shift = torch.repeat_interleave(starts[a:b] - sub_indptr[a:b], d[a:b])
+        e = shift + torch.arange(lo, hi, dtype=torch.int64, device=device)
+        sub_indices[lo:hi] = ((_hash(seed * 4 + 1, e) & 0x7FFFFFFFFFFFFFFF) % num_nodes).to(id_dtype)
+        if weights:
+            sub_probs[lo:hi] = ((_hash(seed * 4 + 2, e) & 1023) + 1).to(torch.float32) / 256.0
+        del shift, e
+    return nids.to(id_dtype), sub_indptr, sub_indices, sub_probs
+
+
 def make_features(num_nodes, dim, dtype=torch.float32, seed=0, device="cpu", chunk=1 << 20,
                   nids=None):
     """Feature table of all nodes (or of `nids`, e.g. a shard) generated chunk by chunk."""

@@ -116,6 +116,10 @@ int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_table, int64_
                     const void *loc_table, int64_t capacity, int itype, const void *nids,
                     int64_t n, void *out, int algo, void *stream);
 
+/* modulo-sharded gather (extension): every row cached, row n = shard n % world, slot n / world. */
+int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_bytes, int itype,
+                        const void *nids, int64_t n, void *out, int algo, void *stream);
+
 /* ------------------------------------------------------------------ sub-CSR extraction
  * replaces ExtractIndptr / ExtractEdgeData (src/sampling/cuda/utils.cu:12-101).
  * indptr / edge_data may be device or mapped host memory. */
@@ -146,6 +150,10 @@ typedef struct {
   const dgs_p2p_server_t *p2p_probs;
   const void *loc_table;
   int64_t loc_capacity;
+  /* > 0 (= p2p world size): every node is cached and node n lives on device n % world at shard
+   * slot n / world - the owner is computed, loc_table is not read (extension; the layout of the
+   * sharded benchmarks). */
+  int32_t loc_mod_world;
 } dgs_graph_t;
 
 /* Workspace size (bytes) for a call over at most max_seeds seeds.  The first 256 bytes must be

@@ -136,6 +136,30 @@ def main():
         assert ent.get(qq, (-1, -1)) == (d, i)
     dist.barrier()
     fs.close()
+
+    # ---- exact modulo sharding (node n on GPU n % world, slot n // world): arithmetic owner, no
+    # location table; shards generated directly on the device (from_device_shard[s] extensions)
+    nids, sp, si, spr = dgs_synth.make_shard(N, E, rank, world, seed=31, device=dev, weights=True, classes=8)
+    for bias in (False, True):
+        smp = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, spr if bias else None, nids, N, rank)
+        assert smp._mod_world == world and smp._table is None
+        exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(ip), t2n(ix), 2)
+        for fan in ([-1, -1], [maxdeg, maxdeg]):
+            out = smp._CAPI_sample_node_classifiction(seeds, fan, False)
+            for a, e in zip(out, exp):
+                for x, z in zip(a, e):
+                    assert np.array_equal(t2n(x), z)
+        a = smp._CAPI_sample_node_classifiction(seeds, [15, 10, 5], False, rng_seed=3)
+        b = smp._CAPI_sample_node_classifiction(seeds, [15, 10, 5], False, rng_seed=3)
+        assert all(torch.equal(x, y) for u, v in zip(a, b) for x, y in zip(u, v))
+        smp.close()
+    fsm = dgs.classes.P2PCacheFeatureServer.from_device_shard(
+        dgs_synth.feature_rows(nids, D), nids, N, rank)
+    assert fsm._mod_world == world
+    for algo in (0, 1, 2):
+        assert torch.equal(fsm._CAPI_get_feature(q, algo).cpu(), feat[q.cpu()])
+    dist.barrier()
+    fsm.close()
     print(f"RANK {rank} OK", flush=True)
     dist.destroy_process_group()
 

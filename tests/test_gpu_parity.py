@@ -552,6 +552,67 @@ def test_huge_num_picks_uses_output_scratch(dgs, cuda, bias):
     _check_sample(seeds, indptr, indices, row, col, k, False)
 
 
+@pytest.mark.parametrize("bias", [False, True])
+def test_modulo_sharded_fast_path_single_rank(dgs, cuda, bias):
+    """cache_nids == arange(N): every node cached in id order -> the owner is arithmetic and no
+    location table is built; results must equal the hash path and the oracle, through both the
+    CPU-tensor constructors and the from_device_shard(s) extensions."""
+    N, D = 4000, 100
+    indptr, indices, probs = dgs_synth.make_csr(N, 90000, seed=41, weights=bias, classes=6)
+    feat = dgs_synth.feature_rows(torch.arange(N), D)
+    maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    ip, ix = indptr.pin_memory(), indices.pin_memory()
+    pr = probs.pin_memory() if bias else torch.Tensor()
+    allnodes = torch.arange(N)
+    s1 = dgs.classes.P2PCacheSampler(ip, ix, pr, allnodes, 0)
+    assert s1._mod_world == 1 and s1._table is None
+    nids, sp, si, spr = dgs_synth.make_shard(N, 90000, 0, 1, seed=41, device=cuda, weights=bias, classes=6)
+    s2 = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, spr, nids, N, 0)
+    assert s2._mod_world == 1
+    seeds = torch.randperm(N, generator=torch.Generator().manual_seed(3))[:200].to(cuda)
+    exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), 2)
+    for smp in (s1, s2):
+        for fan in ([maxdeg, maxdeg], [-1, -1]):
+            out = smp._CAPI_sample_node_classifiction(seeds, fan, False)
+            for a, e in zip(out, exp):
+                for x, z in zip(a, e):
+                    assert np.array_equal(t2n(x), z)
+    r1 = s1._CAPI_sample_node_classifiction(seeds, [10, 5], False, rng_seed=9)
+    r2 = s2._CAPI_sample_node_classifiction(seeds, [10, 5], False, rng_seed=9)
+    assert all(torch.equal(a, b) for x, y in zip(r1, r2) for a, b in zip(x, y))
+    key, idx, dev = s1._CAPI_get_local_cache_hashmap_tensors()   # built on demand
+    assert sorted(key[key >= 0].tolist()) == list(range(N))
+    f1 = dgs.classes.P2PCacheFeatureServer(feat.pin_memory(), allnodes, 0)
+    f2 = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat.to(cuda), allnodes.to(cuda), N, 0)
+    assert f1._mod_world == 1 and f2._mod_world == 1
+    q = torch.randint(0, N, (30000,), generator=torch.Generator().manual_seed(4)).to(cuda)
+    for fs in (f1, f2):
+        for algo in (1, 2):
+            assert torch.equal(fs._CAPI_get_feature(q, algo).cpu(), feat[q.cpu()])
+
+
+def test_from_device_shard_with_hash_table(dgs, cuda):
+    """from_device_shard(s) with a partial cache (hash path) and a pinned host fallback."""
+    N, D = 3000, 36
+    indptr, indices, _ = dgs_synth.make_csr(N, 50000, seed=42, classes=6)
+    feat = dgs_synth.feature_rows(torch.arange(N), D)
+    cache = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:1000]
+    sub = oracle.extract_indptr(t2n(cache), t2n(indptr))
+    sub_idx = oracle.extract_edge_data(t2n(cache), t2n(indptr), sub, t2n(indices))
+    smp = dgs.classes.P2PCacheSampler.from_device_shards(
+        torch.from_numpy(sub).to(cuda), torch.from_numpy(sub_idx).to(cuda), None, cache.to(cuda), N, 0,
+        cpu_indptr=indptr.pin_memory(), cpu_indices=indices.pin_memory())
+    assert smp._mod_world == 0
+    seeds = torch.arange(0, N, 7).to(cuda)
+    out = smp._CAPI_sample_node_classifiction(seeds, [-1], False)[0]
+    e = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), 1)[0]
+    assert all(np.array_equal(t2n(x), z) for x, z in zip(out, e))
+    fs = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat[cache].to(cuda), cache.to(cuda), N, 0,
+                                                             cpu_data=feat.pin_memory())
+    q = torch.randint(0, N, (9000,), generator=torch.Generator().manual_seed(2)).to(cuda)
+    assert torch.equal(fs._CAPI_get_feature(q).cpu(), feat[q.cpu()])
+
+
 def test_p2p_server_single_rank(dgs, cuda):
     t = torch.arange(24, dtype=torch.float32, device=cuda).reshape(6, 4)
     srv = dgs.classes.TensorP2PServer(t)
