@@ -72,6 +72,22 @@ int dgs_host_register(void *host_ptr, size_t nbytes) {
   DGS_CUDA_OK(e);
   return 0;
 }
+int dgs_enable_peer_access(int peer_device) {
+  int dev = 0;
+  DGS_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == peer_device) return 0;
+  int can = 0;
+  DGS_CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  DGS_REQUIRE(can, "device %d cannot access device %d", dev, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return 0;
+  }
+  DGS_CUDA_OK(e);
+  return 0;
+}
+
 int dgs_host_unregister(void *host_ptr) {
   DGS_REQUIRE(host_ptr != nullptr, "dgs_host_unregister: null pointer");
   cudaError_t e = cudaHostUnregister(host_ptr);

@@ -10,9 +10,14 @@
 // path is in-kernel NVLink peer loads through the pointer tables created here.
 // Differences from the reference, on purpose: exchanges go through ordinary device buffers (the
 // reference cudaHostRegister()s stack memory and hands it to NCCL, tensor_p2p_cache.cc:54-63).
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
 
+#include <thread>
 #include <vector>
 
 #include "dgs_common.cuh"
@@ -84,6 +89,8 @@ static int load_nccl() {
   } while (0)
 
 struct NcclCtx {
+  uint64_t uid_hash = 0;   // names the fd-exchange sockets of this communicator
+  int64_t serial = 0;      // p2p servers created so far (same on every rank: creation is collective)
   bool ready = false;
   ncclComm_t comm = nullptr;
   int rank = 0;
@@ -93,6 +100,251 @@ struct NcclCtx {
   size_t scratch_bytes = 0;
 };
 static NcclCtx g_ctx;
+
+}  // namespace dgsb
+
+extern "C" int dgs_nccl_barrier(void);
+extern "C" int dgs_nccl_allgather_i64(int64_t value, int64_t *out_host);
+
+namespace dgsb {
+
+// ------------------------------------------------------------------------------------------
+// VMM shards: cuMemCreate + POSIX-fd export, fds passed between the ranks of the box over
+// abstract unix sockets (SCM_RIGHTS), cuMemMap on every rank.  Measured on B200: in-kernel random
+// 512-B row reads from a 28 GB peer shard run at ~75 GB/s through a legacy cudaIpcOpenMemHandle
+// mapping but at 640-740 GB/s through a cuMemMap / plain peer mapping (tools/peer_probe.py), so
+// the legacy CUDA-IPC path of the reference (tensor_p2p_cache.cc:52-73) is only the fallback.
+struct DrvApi {
+  bool ok = false;
+  CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+};
+static DrvApi g_drv;
+
+static bool load_drv() {
+  if (g_drv.ok) return true;
+  cudaFree(0);
+#define DRV(field, name)                                                                      \
+  do {                                                                                        \
+    void *fn = nullptr;                                                                       \
+    cudaDriverEntryPointQueryResult q;                                                        \
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {    \
+      cudaGetLastError();                                                                     \
+      return false;                                                                           \
+    }                                                                                         \
+    g_drv.field = (decltype(g_drv.field))fn;                                                  \
+  } while (0)
+  DRV(MemGetAllocationGranularity, "cuMemGetAllocationGranularity");
+  DRV(MemCreate, "cuMemCreate");
+  DRV(MemAddressReserve, "cuMemAddressReserve");
+  DRV(MemMap, "cuMemMap");
+  DRV(MemSetAccess, "cuMemSetAccess");
+  DRV(MemExportToShareableHandle, "cuMemExportToShareableHandle");
+  DRV(MemImportFromShareableHandle, "cuMemImportFromShareableHandle");
+  DRV(MemUnmap, "cuMemUnmap");
+  DRV(MemRelease, "cuMemRelease");
+  DRV(MemAddressFree, "cuMemAddressFree");
+#undef DRV
+  g_drv.ok = true;
+  return true;
+}
+
+static void sock_name(sockaddr_un *addr, socklen_t *len, int64_t serial, int rank) {
+  memset(addr, 0, sizeof(*addr));
+  addr->sun_family = AF_UNIX;
+  // abstract namespace (leading NUL): nothing to unlink, private to the box
+  int n = snprintf(addr->sun_path + 1, sizeof(addr->sun_path) - 1, "dgs_b200_%016llx_%lld_%d",
+                   (unsigned long long)g_ctx.uid_hash, (long long)serial, rank);
+  *len = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+
+static int send_fd(int sock, int fd) {
+  char dummy = 'x', ctrl[CMSG_SPACE(sizeof(int))];
+  memset(ctrl, 0, sizeof(ctrl));
+  iovec iov{&dummy, 1};
+  msghdr msg{};
+  msg.msg_iov = &iov;
+  msg.msg_iovlen = 1;
+  msg.msg_control = ctrl;
+  msg.msg_controllen = sizeof(ctrl);
+  cmsghdr *c = CMSG_FIRSTHDR(&msg);
+  c->cmsg_level = SOL_SOCKET;
+  c->cmsg_type = SCM_RIGHTS;
+  c->cmsg_len = CMSG_LEN(sizeof(int));
+  memcpy(CMSG_DATA(c), &fd, sizeof(int));
+  return sendmsg(sock, &msg, 0) == 1 ? 0 : -1;
+}
+
+static int recv_fd(int sock) {
+  char dummy, ctrl[CMSG_SPACE(sizeof(int))];
+  iovec iov{&dummy, 1};
+  msghdr msg{};
+  msg.msg_iov = &iov;
+  msg.msg_iovlen = 1;
+  msg.msg_control = ctrl;
+  msg.msg_controllen = sizeof(ctrl);
+  if (recvmsg(sock, &msg, 0) != 1) return -1;
+  cmsghdr *c = CMSG_FIRSTHDR(&msg);
+  if (!c || c->cmsg_type != SCM_RIGHTS) return -1;
+  int fd;
+  memcpy(&fd, CMSG_DATA(c), sizeof(int));
+  return fd;
+}
+
+// every rank serves its own fd to the world-1 peers and fetches theirs; returns 0 on success
+static int exchange_fds(int my_fd, int world, int rank, int64_t serial, int *peer_fds) {
+  sockaddr_un addr;
+  socklen_t alen;
+  sock_name(&addr, &alen, serial, rank);
+  int srv = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (srv < 0 || bind(srv, (sockaddr *)&addr, alen) != 0 || listen(srv, world) != 0) {
+    if (srv >= 0) close(srv);
+    return -1;
+  }
+  int srv_err = 0;
+  std::thread server([&]() {
+    for (int i = 0; i < world - 1; ++i) {
+      int c = accept(srv, nullptr, nullptr);
+      if (c < 0 || send_fd(c, my_fd) != 0) srv_err = 1;
+      if (c >= 0) close(c);
+    }
+  });
+  int err = 0;
+  if (dgs_nccl_barrier()) err = 1;  // every rank is listening
+  for (int p = 0; p < world && !err; ++p) {
+    if (p == rank) continue;
+    sockaddr_un pa;
+    socklen_t pl;
+    sock_name(&pa, &pl, serial, p);
+    int c = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (c < 0 || connect(c, (sockaddr *)&pa, pl) != 0) {
+      err = 1;
+    } else {
+      peer_fds[p] = recv_fd(c);
+      if (peer_fds[p] < 0) err = 1;
+    }
+    if (c >= 0) close(c);
+  }
+  if (err) {
+    // unblock our own server thread: connect to ourselves for the accepts that will never come
+    // (peers that failed); best effort - a failed exchange is fatal for the caller anyway
+    shutdown(srv, SHUT_RDWR);
+  }
+  server.join();
+  close(srv);
+  return (err || srv_err) ? -1 : 0;
+}
+
+static int vmm_map(dgs_p2p_server *s, int slot, int dev, CUmemGenericAllocationHandle h, size_t size,
+                   size_t gran) {
+  CUdeviceptr ptr = 0;
+  if (g_drv.MemAddressReserve(&ptr, size, gran, 0, 0) != CUDA_SUCCESS) return -1;
+  if (g_drv.MemMap(ptr, size, 0, h, 0) != CUDA_SUCCESS) {
+    g_drv.MemAddressFree(ptr, size);
+    return -1;
+  }
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (g_drv.MemSetAccess(ptr, size, &acc, 1) != CUDA_SUCCESS) {
+    g_drv.MemUnmap(ptr, size);
+    g_drv.MemAddressFree(ptr, size);
+    return -1;
+  }
+  s->ptrs[slot] = (void *)ptr;
+  s->vmm_handle[slot] = (unsigned long long)h;
+  s->vmm_size[slot] = (int64_t)size;
+  return 0;
+}
+
+// returns 0 on success, 1 when the VMM path is unavailable (caller falls back to legacy IPC),
+// >= 2 on a hard error (set_error called)
+static int vmm_create(dgs_p2p_server *s, const void *dev_src, int64_t nbytes) {
+  if (getenv("DGS_P2P_LEGACY_IPC")) return 1;  // (set it on every rank or on none)
+  int dev = 0;
+  size_t gran = 0, size = 0;
+  CUmemGenericAllocationHandle h = 0;
+  int fd = -1;
+  int have = 0;
+  CUmemAllocationProp prop{};
+  if (load_drv() && cudaGetDevice(&dev) == cudaSuccess) {
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    if (g_drv.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS &&
+        gran > 0) {
+      size = ((size_t)nbytes + gran - 1) / gran * gran;
+      have = (g_drv.MemCreate(&h, size, &prop, 0) == CUDA_SUCCESS) ? 1 : 0;
+      if (have && g_drv.MemExportToShareableHandle(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS)
+        have = 0;
+    }
+  }
+  // all ranks must take the same path: agree on availability
+  std::vector<int64_t> flags(s->world);
+  if (dgs_nccl_allgather_i64(have, flags.data())) return 2;
+  bool all = true;
+  for (int i = 0; i < s->world; ++i) all = all && flags[i] == 1;
+  if (!all) {
+    if (fd >= 0) close(fd);
+    if (h) g_drv.MemRelease(h);
+    return 1;
+  }
+  s->vmm = 1;
+  if (vmm_map(s, s->rank, dev, h, size, gran) != 0) {
+    set_error("dgs_p2p_server_create: cuMemMap of the local shard (%zu bytes) failed", size);
+    return 2;
+  }
+  if (dev_src) {
+    cudaError_t e = cudaMemcpy(s->ptrs[s->rank], dev_src, (size_t)nbytes, cudaMemcpyDefault);
+    if (e != cudaSuccess) {
+      set_error("dgs_p2p_server_create: copy failed: %s", cudaGetErrorString(e));
+      return 2;
+    }
+  }
+  std::vector<int64_t> sizes(s->world), msizes(s->world);
+  if (dgs_nccl_allgather_i64(nbytes, sizes.data())) return 2;
+  if (dgs_nccl_allgather_i64((int64_t)size, msizes.data())) return 2;
+  std::vector<int> fds(s->world, -1);
+  const int64_t serial = g_ctx.serial++;
+  if (exchange_fds(fd, s->world, s->rank, serial, fds.data()) != 0) {
+    set_error("dgs_p2p_server_create: fd exchange over unix sockets failed");
+    close(fd);
+    return 2;
+  }
+  close(fd);
+  for (int i = 0; i < s->world; ++i) {
+    s->nbytes[i] = sizes[i];
+    if (i == s->rank) continue;
+    CUmemGenericAllocationHandle ph = 0;
+    if (g_drv.MemImportFromShareableHandle(&ph, (void *)(uintptr_t)fds[i], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS ||
+        vmm_map(s, i, dev, ph, (size_t)msizes[i], gran) != 0) {
+      set_error("dgs_p2p_server_create: importing / mapping the shard of rank %d failed", i);
+      return 2;
+    }
+    close(fds[i]);
+  }
+  if (dgs_nccl_barrier()) return 2;
+  return 0;
+}
+
+static void vmm_destroy(dgs_p2p_server *s) {
+  for (int i = 0; i < s->world; ++i) {
+    if (!s->ptrs[i]) continue;
+    g_drv.MemUnmap((CUdeviceptr)s->ptrs[i], (size_t)s->vmm_size[i]);
+    g_drv.MemAddressFree((CUdeviceptr)s->ptrs[i], (size_t)s->vmm_size[i]);
+    g_drv.MemRelease((CUmemGenericAllocationHandle)s->vmm_handle[i]);
+  }
+}
 
 }  // namespace dgsb
 
@@ -117,6 +369,8 @@ int dgs_nccl_set(int nranks, const int64_t id[16], int rank) {
   if (load_nccl()) return 1;
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
+  g_ctx.uid_hash = 1469598103934665603ull;
+  for (int i = 0; i < 16; ++i) g_ctx.uid_hash = (g_ctx.uid_hash ^ (uint64_t)id[i]) * 1099511628211ull;
   DGS_NCCL_OK(g_api.CommInitRank(&g_ctx.comm, nranks, uid, rank));
   g_ctx.rank = rank;
   g_ctx.world = nranks;
@@ -202,6 +456,19 @@ int dgs_p2p_server_create(const void *dev_src, int64_t nbytes, dgs_p2p_server_t 
   s->world = g_ctx.world;
   s->rank = g_ctx.rank;
   s->owns_local = 1;
+  if (s->world > 1) {
+    const int rc = vmm_create(s, dev_src, nbytes);
+    if (rc == 0) {
+      *out = s;
+      return 0;
+    }
+    if (rc >= 2) {
+      delete s;
+      return rc;
+    }
+    memset(s->ptrs, 0, sizeof(s->ptrs));  // VMM unavailable on some rank: legacy CUDA IPC below
+    s->vmm = 0;
+  }
   void *local = nullptr;
   // raw cudaMalloc (not the torch caching allocator): IPC handles need a whole allocation.
   cudaError_t e = cudaMalloc(&local, (size_t)nbytes);
@@ -273,6 +540,14 @@ int dgs_p2p_server_rank(const dgs_p2p_server_t *s) { return s ? s->rank : -1; }
 
 int dgs_p2p_server_destroy(dgs_p2p_server_t *s, int barrier) {
   if (!s) return 0;
+  if (s->vmm) {
+    int rc = 0;
+    cudaDeviceSynchronize();
+    if (barrier && s->world > 1) rc = dgs_nccl_barrier();  // nobody reads our shard any more
+    vmm_destroy(s);
+    delete s;
+    return rc;
+  }
   if (s->ipc_opened) {
     for (int i = 0; i < s->world; ++i)
       if (i != s->rank && s->ptrs[i]) cudaIpcCloseMemHandle(s->ptrs[i]);

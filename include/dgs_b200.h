@@ -50,6 +50,9 @@ void dgs_seed(uint64_t seed);
  * replaces TensorPinMemory / TensorUnpinMemory  (src/common/pin_memory.cc:7-19). */
 int dgs_host_register(void *host_ptr, size_t nbytes);
 int dgs_host_unregister(void *host_ptr);
+/* single-process multi-GPU use (tests / probes): let kernels on the current device dereference
+ * memory of peer_device (cudaDeviceEnablePeerAccess). */
+int dgs_enable_peer_access(int peer_device);
 
 /* ------------------------------------------------------------------ NCCL context
  * replaces nccl::GetUniqueId / SetNCCL / NCCLContext::{Barrier_, NCCLTensorAllGather_}

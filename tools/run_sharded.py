@@ -73,14 +73,12 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     edges = rows = 0
-    fronts = []
     e0.record()
     for i in range(args.steps):
         blocks = smp._CAPI_sample_node_classifiction(seeds[5 + i], fan)
         x = fs._CAPI_get_feature(blocks[-1][1])
         edges += sum(b[2].numel() for b in blocks)
         rows += x.shape[0]
-        fronts.append(blocks[-1][1])
     e1.record()
     barrier()
     ms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX)
@@ -88,15 +86,18 @@ def main():
     # extract-only microbench: R random ids per rank, back-to-back launches
     g = torch.Generator().manual_seed(rank)
     q = [torch.randint(0, N, (args.extract_rows,), generator=g).to(dev) for _ in range(4)]
-    outs = [fs._CAPI_get_feature(q[i % 4]) for i in range(8)]   # untimed: allocator pools
-    del outs
-    barrier()
-    e0.record()
-    outs = [fs._CAPI_get_feature(q[i % 4]) for i in range(8)]
-    e1.record()
-    barrier()
-    xms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX) / 8
-    del outs
+    xms_algo = {}
+    for algo in (1, 2):
+        outs = [fs._CAPI_get_feature(q[i % 4], algo) for i in range(8)]   # untimed: allocator pools
+        del outs
+        barrier()
+        e0.record()
+        outs = [fs._CAPI_get_feature(q[i % 4], algo) for i in range(8)]
+        e1.record()
+        barrier()
+        xms_algo[algo] = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX) / 8
+        del outs
+    xms = xms_algo[1]
     # sampling-only, back to back
     keep = [smp._pipe.enqueue_only(seeds[i], fan) for i in range(3)]
     barrier()
@@ -117,7 +118,7 @@ def main():
             "rows_per_step_per_gpu": tot_rows / world / args.steps,
             "edges_per_step_per_gpu": tot_edges / world / args.steps,
             "sample_kernel_ms": sms,
-            "extract_only": {"rows_per_gpu": R, "ms": xms,
+            "extract_only": {"rows_per_gpu": R, "ms": xms, "ms_tma": xms_algo[2],
                              "algorithmic_gbps_per_gpu": R * (2 * row_bytes + 8) / (xms * 1e-3) / 1e9,
                              "peer_load_gbps_per_gpu": R * row_bytes * (world - 1) / world / (xms * 1e-3) / 1e9,
                              "nvlink_peak_gbps": 900, "nvlink_measured_peer_copy_gbps": 770},
