@@ -73,16 +73,50 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     edges = rows = 0
+    t_s = t_x = 0.0
+    evs = []
     e0.record()
     for i in range(args.steps):
+        ta = time.perf_counter()
         blocks = smp._CAPI_sample_node_classifiction(seeds[5 + i], fan)
+        tb = time.perf_counter()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
         x = fs._CAPI_get_feature(blocks[-1][1])
+        eb.record()
+        evs.append((ea, eb))
+        tc = time.perf_counter()
+        t_s += tb - ta
+        t_x += tc - tb
         edges += sum(b[2].numel() for b in blocks)
         rows += x.shape[0]
     e1.record()
     barrier()
     ms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+    host_sample_us = reduce(t_s / args.steps * 1e6, dist.ReduceOp.MAX)
+    host_extract_us = reduce(t_x / args.steps * 1e6, dist.ReduceOp.MAX)
+    gpu_extract_us = reduce(sum(a.elapsed_time(b) for a, b in evs) / args.steps * 1e3, dist.ReduceOp.MAX)
     tot_edges, tot_rows = reduce(edges, dist.ReduceOp.SUM), reduce(rows, dist.ReduceOp.SUM)
+    # host-side diagnostics of the extract call (max over ranks)
+    fr = blocks[-1][1].clone()
+    torch.cuda.synchronize()
+    ta = time.perf_counter()
+    for i in range(20):
+        tmp = torch.empty((fr.numel(), D), dtype=dt, device=dev)
+    diag_empty_us = reduce((time.perf_counter() - ta) / 20 * 1e6, dist.ReduceOp.MAX)
+    from dgs import _lib
+    from dgs._util import stream as _stream
+    out = torch.empty((fr.numel(), D), dtype=dt, device=dev)
+    torch.cuda.synchronize()
+    e0.record()
+    ta = time.perf_counter()
+    for i in range(20):
+        _lib.check(_lib.lib().dgs_extract_sharded(fs.gpu_features_._handle, fs._row_bytes, 1, fr.data_ptr(),
+                                                  fr.numel(), out.data_ptr(), 0, _stream()))
+    diag_call_us = reduce((time.perf_counter() - ta) / 20 * 1e6, dist.ReduceOp.MAX)
+    e1.record()
+    torch.cuda.synchronize()
+    diag_gpu_us = reduce(e0.elapsed_time(e1) / 20 * 1e3, dist.ReduceOp.MAX)
     # extract-only microbench: R random ids per rank, back-to-back launches
     g = torch.Generator().manual_seed(rank)
     q = [torch.randint(0, N, (args.extract_rows,), generator=g).to(dev) for _ in range(4)]
@@ -117,7 +151,10 @@ def main():
             "extract_gbps_in_step": tot_rows * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
             "rows_per_step_per_gpu": tot_rows / world / args.steps,
             "edges_per_step_per_gpu": tot_edges / world / args.steps,
-            "sample_kernel_ms": sms,
+            "sample_kernel_ms": sms, "host_sample_call_us_max": host_sample_us,
+            "host_extract_call_us_max": host_extract_us, "gpu_extract_in_step_us_max": gpu_extract_us, "host_cpus": len(os.sched_getaffinity(0)),
+            "diag": {"torch_empty_us": diag_empty_us, "extract_c_call_us": diag_call_us,
+                     "extract_gpu_frontier_us": diag_gpu_us},
             "extract_only": {"rows_per_gpu": R, "ms": xms, "ms_tma": xms_algo[2],
                              "algorithmic_gbps_per_gpu": R * (2 * row_bytes + 8) / (xms * 1e-3) / 1e9,
                              "peer_load_gbps_per_gpu": R * row_bytes * (world - 1) / world / (xms * 1e-3) / 1e9,
