@@ -187,7 +187,7 @@ def run_reference(args, fan_out):
         "batches_per_sec": cb["batches_per_sec"], "extract_gbps": cb["extract_gbps"],
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------- B200 arm
@@ -292,12 +292,13 @@ def run_b200(args, fan_out):
     launches0 = dgs.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    edges = rows = hop_seeds = 0
+    edges = rows = hop_seeds = uniq = 0
     e0.record()
     for i in range(W, W + K):
         blocks, x = step_device(i)
         edges += sum(b[2].numel() for b in blocks)
         hop_seeds += sum(b[0].numel() for b in blocks)
+        uniq += sum(b[1].numel() for b in blocks)
         rows += x.shape[0]
     e1.record()
     barrier()
@@ -337,7 +338,8 @@ def run_b200(args, fan_out):
     torch.cuda.synchronize()
     sm_ms = x0.elapsed_time(x1)
     del keep
-    sm_bytes = 24.0 * (hop_seeds + edges)   # 24 * (S + nnz) per hop
+    # SURVEY 8d, summed over hops: sampling 24 (S + nnz) + relabel 8 (S + nnz) + 32 nnz + 8 U
+    sm_bytes = 24.0 * (hop_seeds + edges) + 8.0 * (hop_seeds + edges) + 32.0 * edges + 8.0 * uniq
 
     # ---- end-to-end timing through the plugin API with host seeds / host result ("e2e")
     for i in range(W):
@@ -380,7 +382,7 @@ def run_b200(args, fan_out):
                                              "cooperative launch per batch)",
                    "achieved": sm_gbs, "peak": peak, "unit": "GB/s", "frac": sm_gbs / peak,
                    "peak_source": peak_src, "traffic": traffic.get("sample"),
-                   "algorithmic_bytes": "24 * (seeds + sampled edges) summed over hops",
+                   "algorithmic_bytes": "sum over hops of 24 (S + nnz) [sample] + 8 (S + nnz) + 32 nnz + 8 U [relabel]",
                    "avg_launch_ms": sm_ms / K,
                    "note": "latency-bound at batch %d: dependent load / atomic chains and 9 grid "
                            "barriers, not bandwidth (DESIGN.md section 5)" % args.batch}
@@ -412,19 +414,51 @@ def run_b200(args, fan_out):
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["batches_per_sec"] = cb["batches_per_sec"]
         line["cpu_baseline"]["extract_gbps"] = cb["extract_gbps"]
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class _OnlyJsonOnStdout:
+    """Libraries (NCCL's version banner, torch warnings) sometimes write to fd 1; the contract is
+    ONE JSON line on stdout, so fd 1 is pointed at stderr for the whole run and the JSON line is
+    written to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit(obj):
+    OUT.emit(json.dumps(obj))
+
+
 def main():
+    global OUT
     args = parse_args()
     fan_out = [int(x) for x in args.fan_out.split(",")]
-    if args.impl == "reference":
-        run_reference(args, fan_out)
-    else:
-        run_b200(args, fan_out)
+    with _OnlyJsonOnStdout() as out:
+        OUT = out
+        if args.impl == "reference":
+            run_reference(args, fan_out)
+        else:
+            run_b200(args, fan_out)
 
 
 if __name__ == "__main__":

@@ -529,6 +529,74 @@ def test_sampler_blocks_random_properties(dgs, cuda, bias):
     assert all(torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) for a, b in zip(out, again))
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+def test_fused_blocks_edge_cases(dgs, cuda, idt):
+    """Fused whole-batch path: duplicate seeds, fan-out 0, 1 and 4 hops, int32 ids, replace=True,
+    tiny and non-multiple-of-tile seed counts - against the oracle's layer loop (copy path) or the
+    hop invariants (random path)."""
+    N = 2500
+    indptr, indices, _ = dgs_synth.make_csr(N, 30000, seed=17, classes=6, id_dtype=idt)
+    maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda))
+    g = torch.Generator().manual_seed(5)
+    for n_seeds in (1, 7, 129, 1000):
+        seeds = torch.randint(0, N, (n_seeds,), generator=g).to(idt)      # duplicates allowed
+        for L in (1, 4) if n_seeds <= 7 else (2,):
+            exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), L)
+            out = smp._CAPI_sample_node_classifiction(seeds.to(cuda), [maxdeg] * L, False)
+            assert len(out) == L
+            for a, e in zip(out, exp):
+                assert a[0].dtype == idt
+                for x, z in zip(a, e):
+                    assert np.array_equal(t2n(x), z)
+    seeds = torch.randperm(N, generator=g)[:300].to(idt)
+    # fan-out 0: no edges, frontier = seeds
+    out = smp._CAPI_sample_node_classifiction(seeds.to(cuda), [0], False)
+    assert out[0][2].numel() == 0 and torch.equal(out[0][1].cpu(), seeds)
+    out = smp._CAPI_sample_node_classifiction(seeds.to(cuda), [3, 0], False)   # hop 1 k=0, hop 2 k=3
+    assert out[0][2].numel() == 0 and torch.equal(out[1][0].cpu(), seeds)
+    # with replacement through the fused path
+    out = smp._CAPI_sample_node_classifiction(seeds.to(cuda), [4, 3], True, rng_seed=2)
+    cur = seeds
+    for (s_, f_, r_, c_), k in zip(out, (3, 4)):
+        f = f_.cpu()
+        _check_sample(cur, indptr, indices, cur[r_.cpu().long()], f[c_.cpu().long()], k, True)
+        eu, _ = oracle.relabel([t2n(cur), t2n(f[c_.cpu().long()])], [])
+        assert np.array_equal(t2n(f), eu)
+        cur = f
+
+
+def test_fused_blocks_cooperative_equals_multi_kernel(dgs, cuda, monkeypatch):
+    """The cooperative single-launch kernel and the 3-kernels-per-hop path share their phase code
+    and RNG counters: identical outputs for the same seed (DGS_BLOCKS_MODE is read once per
+    process, so the comparison runs in a child process)."""
+    import subprocess, sys, os, json
+    code = r"""
+import sys, os, hashlib
+sys.path.insert(0, os.path.join(os.getcwd(), 'dist-gnn_b200'))
+import torch, dgs, dgs_synth
+ip, ix, pr = dgs_synth.make_csr(20000, 500000, seed=12, weights=True)
+seeds = torch.randperm(20000, generator=torch.Generator().manual_seed(2))[:1024].cuda()
+h = hashlib.sha256()
+for probs in (None, pr.cuda()):
+    s = dgs.classes.CSRSampler(ip.cuda(), ix.cuda(), probs)
+    for rep in (False, True):
+        for _ in range(2):
+            for blk in s._CAPI_sample_node_classifiction(seeds, [15, 10, 5], rep, rng_seed=11):
+                for t in blk:
+                    h.update(t.cpu().numpy().tobytes())
+print(h.hexdigest())
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for mode in ("coop", "multi"):
+        env = dict(os.environ, DGS_BLOCKS_MODE=mode)
+        p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        digests.append(p.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
+
+
 @pytest.mark.parametrize("bias", [False, True])
 def test_huge_num_picks_uses_output_scratch(dgs, cuda, bias):
     """num_picks far beyond what shared memory holds (the reference asserts num_picks <= 32 for the
