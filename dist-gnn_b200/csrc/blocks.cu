@@ -45,7 +45,7 @@ namespace dgsb {
 
 constexpr int kBkWarps = 8;
 constexpr int kBkThreads = 256;
-constexpr int kBkTile = 64;  // seeds per rank tile
+constexpr int kBkTile = 128;  // seeds per rank tile
 
 struct __align__(16) RlSlot {
   long long key;       // -1 empty
@@ -276,8 +276,9 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
 // code runs as a stand-alone kernel (multi-kernel path) or as one phase of the cooperative
 // whole-batch kernel (phases separated by grid barriers).  Data produced by other CTAs in an
 // earlier phase is read with ld.global.cg (L2), never through a possibly stale L1 line.
-constexpr int kPkSeeds = 128;  // seeds per pick tile
-constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick / emit phases
+constexpr int kPkSeeds = 128;  // seeds per pick tile (256 was slower on B200: 4 B2 rounds per tile)
+constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase
+constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
 
 // Seeds per pick tile: up to 128, fewer when the hop is small so that every CTA of the grid gets
@@ -307,7 +308,7 @@ struct PosEmit {
   __device__ __forceinline__ void operator()(int j, IdT v) { p[j] = (unsigned int)v; }
 };
 
-// Pick phase, tile version: a CTA owns 128 seeds.
+// Pick phase, tile version: a CTA owns up to 128 seeds.
 //   A  thread per seed : probe, indptr pair, count, insert the seed id        (128 chains in flight)
 //   B1 selection -> POSITIONS inside the row, kept in shared memory: Floyd's subset sampling run
 //      by one thread per seed for uniform sampling (no memory traffic at all), a warp per seed
@@ -590,13 +591,13 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
   }
   if (k <= 0) return;
   const int64_t E = S * k;
-  for (int64_t base = tid; base < E; base += stride * kPkBatch) {
-    int64_t si[kPkBatch];
-    int jj[kPkBatch];
-    bool ok[kPkBatch];
-    unsigned int pc[kPkBatch], ps[kPkBatch];
+  for (int64_t base = tid; base < E; base += stride * kEmBatch) {
+    int64_t si[kEmBatch];
+    int jj[kEmBatch];
+    bool ok[kEmBatch];
+    unsigned int pc[kEmBatch], ps[kEmBatch];
 #pragma unroll
-    for (int u = 0; u < kPkBatch; ++u) {
+    for (int u = 0; u < kEmBatch; ++u) {
       const int64_t e = base + u * stride;
       ok[u] = false;
       if (e < E) {
@@ -607,9 +608,9 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
         ps[u] = ldcg(cur.pos_seed + si[u]);
       }
     }
-    unsigned int cf[kPkBatch], cr[kPkBatch], sf[kPkBatch], sr[kPkBatch];
+    unsigned int cf[kEmBatch], cr[kEmBatch], sf[kEmBatch], sr[kEmBatch];
 #pragma unroll
-    for (int u = 0; u < kPkBatch; ++u) {
+    for (int u = 0; u < kEmBatch; ++u) {
       if (ok[u]) {
         const int2 c2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[pc[u]].first));
         const int2 s2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[ps[u]].first));
@@ -618,7 +619,7 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
       }
     }
 #pragma unroll
-    for (int u = 0; u < kPkBatch; ++u) {
+    for (int u = 0; u < kEmBatch; ++u) {
       if (ok[u]) {
         const int64_t e = base + u * stride;
         RlSlot sc;
@@ -823,7 +824,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
       default: DGS_BK(kBiasReplace); break;
     }
 #undef DGS_BK
-    if (smem_max > 48 * 1024)
+    if (smem_max > 32 * 1024)  // static shared memory (~8 KB) counts against the 48 KB default
       DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int per_sm = 0;
     DGS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBkThreads, smem_max));
@@ -891,7 +892,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
 #define DGS_TPICK(M)                                                                            \
   do {                                                                                          \
     auto kern = fused_pick_tile_kernel<IdT, ET, M>;                                             \
-    if (smem_tile > 48 * 1024)                                                                  \
+    if (smem_tile > 32 * 1024)                                                                  \
       DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem_tile));                                        \
     kern<<<grid, kBkThreads, smem_tile, st>>>(src, cur_seeds, cur_ub, cur_dev, k, key,          \
@@ -919,7 +920,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
 #define DGS_FPICK(M)                                                                            \
   do {                                                                                          \
     auto kern = fused_pick_kernel<IdT, ET, M>;                                                  \
-    if (smem > 48 * 1024)                                                                       \
+    if (smem > 32 * 1024)                                                                       \
       DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem));                                             \
     kern<<<grid_pick, kBkThreads, smem, st>>>(src, cur_seeds, cur_ub, cur_dev, k, key,          \

@@ -19,7 +19,8 @@ def itype(t, what="ids"):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on the current device."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def ptr(t):
