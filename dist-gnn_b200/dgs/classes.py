@@ -13,6 +13,24 @@ check = _lib.check
 MAX_FUSED_ELEMS = 1 << 28  # ids in the worst-case arena of the fused whole-batch path (2 GiB of int64)
 
 
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _on_device(device):
+    """torch.cuda.device(device), skipped (it costs ~5 us per entry) when already current."""
+    if torch.cuda.current_device() == device.index:
+        return _NOCTX
+    return torch.cuda.device(device)
+
+
 def _barrier():
     check(lib().dgs_nccl_barrier(), "barrier")
 
@@ -253,7 +271,7 @@ class _BlockPipeline:
             rng_seed = l.dgs_randn_uint64()
         if any(k < 0 for k in fan_out) or seeds.numel() == 0:
             return self._sample_per_hop(seeds, fan_out, replace, rng_seed)
-        with torch.cuda.device(self._device):
+        with _on_device(self._device):
             S = seeds.numel()
             pl = self._plan(S, fan_out)
             if pl["ws"] is None:

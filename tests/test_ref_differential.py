@@ -164,3 +164,73 @@ def test_ref_random_sampling_same_support(ref, dgs, cuda):
         br, bc = ref.ops._CAPI_cuda_sample_neighbors_bias(seeds, ip, ix, pr, k, False)
         obr, obc = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds, ip, ix, pr, k, False)
         assert torch.equal(br, obr)
+
+
+def test_ref_gpu_timing_report(ref, dgs, cuda):
+    """Not a pass/fail check of speed: times the reference's own kernels (compiled for sm_100a) and
+    this repo on the SAME B200, same products-shaped workload, same plugin calls
+    (sampler._CAPI_sample_node_classifiction + feature_server._CAPI_get_feature, everything cached
+    on the GPU), and writes gpurun_out/ref_gpu_timing.json (BASELINE.md section 2, row
+    "reference oracle on B200").  Asserts only that both return the same per-hop edge counts."""
+    import json
+    import time
+    N, E, D, dt = dgs_synth.SHAPES["products"]
+    ip, ix, _ = dgs_synth.make_csr(N, E, device=cuda)
+    ft = dgs_synth.make_features(N, D, dt, device=cuda)
+    ipc, ixc, ftc = ip.cpu().pin_memory(), ix.cpu().pin_memory(), ft.cpu().pin_memory()
+    del ip, ix, ft
+    torch.cuda.empty_cache()
+    allnodes = torch.arange(N)
+    fan = [15, 10, 5]
+    seeds = dgs_synth.seed_batches(N, 1024, 40, device=cuda)
+    res = {}
+    counts = {}
+    for name, mod in (("reference", ref), ("this_repo", dgs)):
+        smp = mod.classes.P2PCacheSampler(ipc, ixc, torch.Tensor(), allnodes, 0)
+        fs = mod.classes.P2PCacheFeatureServer(ftc, allnodes.to(cuda), 0)
+        for i in range(5):
+            b = smp._CAPI_sample_node_classifiction(seeds[i], fan, False)
+            fs._CAPI_get_feature(b[-1][1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        edges = rows = 0
+        for i in range(5, 35):
+            b = smp._CAPI_sample_node_classifiction(seeds[i], fan, False)
+            x = fs._CAPI_get_feature(b[-1][1])
+            edges += sum(t[2].numel() for t in b)
+            rows += x.shape[0]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 30
+        # sampling only / extract only (back-to-back launches on saved frontiers)
+        e0.record()
+        fronts = [smp._CAPI_sample_node_classifiction(seeds[i], fan, False)[-1][1].clone() for i in range(5, 35)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1) / 30
+        outs = [fs._CAPI_get_feature(f) for f in fronts]
+        del outs
+        torch.cuda.synchronize()
+        e0.record()
+        outs = [fs._CAPI_get_feature(f) for f in fronts]
+        e1.record()
+        torch.cuda.synchronize()
+        ms_x = e0.elapsed_time(e1) / 30
+        del outs
+        res[name] = {"ms_per_step": ms, "batches_per_sec": 1e3 / ms, "sampled_edges_per_sec": edges / 30 / (ms * 1e-3),
+                     "sampling_ms": ms_s, "extract_ms": ms_x,
+                     "extract_algorithmic_gbps": sum(f.numel() for f in fronts) / 30 * (2 * D * 4 + 8) / (ms_x * 1e-3) / 1e9,
+                     "rows_per_step": rows / 30, "edges_per_step": edges / 30}
+        # deterministic part of the output: hop-1 edge count = sum(min(deg, 5)) for the same seeds
+        b = smp._CAPI_sample_node_classifiction(seeds[0], fan, False)
+        counts[name] = b[0][2].numel()
+        del smp, fs
+        torch.cuda.empty_cache()
+    assert counts["reference"] == counts["this_repo"]
+    for k_ in ("ms_per_step", "sampling_ms", "extract_ms"):
+        res["speedup_" + k_] = res["reference"][k_] / res["this_repo"][k_]
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(res, open(os.path.join(out, "ref_gpu_timing.json"), "w"), indent=1)
+    print(json.dumps(res))
