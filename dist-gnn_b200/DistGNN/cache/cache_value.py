@@ -1,31 +1,50 @@
 """Cache-policy helpers (subset of python/DistGNN/cache/cache_value.py; the selfish / selfless /
 auto cost model is SURVEY.md 8f-3, a later row).  What the data-path benchmarks need is here:
-heat propagation over the sampling fan-out and simple hot-set selection."""
+get_node_heat with the reference's semantics (over the B200 heat kernels) and a simple
+degree-ranked hot set for the cache-ratio sweep."""
 import torch
 
 
-def get_node_heat(indptr, indices, seeds, fan_out, probs=None, capi=None):
-    """Expected visit count of every node when `seeds` are sampled with `fan_out`
-    (cache_value.py:6-53): heat flows seed -> neighbour with min(1, heat * k / deg) per edge, one
-    round per hop (fan_out walked from the back).  All tensors CUDA (or pinned host for the CSR)."""
+def get_node_heat(indptr, indices, node_ids, fan_outs, probs=None, mode="uva", capi=None):
+    """Expected visit counts of every node when `node_ids` are sampled with `fan_outs`
+    (python/DistGNN/cache/cache_value.py:6-53).  Returns (sampling_heat, feature_heat), float32
+    CUDA tensors over all nodes: heat flows seed -> neighbour with min(1, heat * k / deg) per edge
+    (weight-proportional when `probs` is given), one round per hop with fan_outs walked from the
+    back.  mode "uva": the CPU CSR is pinned for the duration and read in place; "cuda": moved."""
+    assert mode in ["uva", "cuda"]
     if capi is None:
         import dgs as capi
-    num_nodes = indptr.numel() - 1
-    dev = seeds.device
-    heat = torch.zeros(num_nodes, dtype=torch.float32, device=dev)
-    heat[seeds] = 1.0
-    total = heat.clone()
-    cur = seeds
-    for k in reversed(list(fan_out)):
+    ops = capi.ops
+    if mode == "uva":
+        for t in (indptr, indices, probs):
+            if t is not None:
+                ops._CAPI_tensor_pin_memory(t)
+    else:
+        indptr, indices = indptr.cuda(), indices.cuda()
+        if probs is not None:
+            probs = probs.cuda()
+    num_nodes = indptr.shape[0] - 1
+    sampling_heat = torch.zeros(num_nodes).cuda()
+    seeds_heat = torch.zeros(num_nodes).cuda()
+    seeds_heat[node_ids] = 1
+    seeds = node_ids.cuda()
+    frontier_heat = torch.zeros(num_nodes).cuda()
+    for num_picks in reversed(list(fan_outs)):
         if probs is None:
-            nxt = capi.ops._CAPI_compute_frontier_heat(cur, indptr, indices, heat, int(k), 0)
+            frontier_heat = ops._CAPI_compute_frontier_heat(seeds, indptr, indices, seeds_heat,
+                                                            num_picks, 0)
         else:
-            nxt = capi.ops._CAPI_compute_frontier_heat_with_bias(cur, indptr, indices, probs, heat,
-                                                                 int(k), 0)
-        total += nxt
-        heat = nxt
-        cur = torch.nonzero(nxt > 0).reshape(-1).to(seeds.dtype)
-    return total
+            frontier_heat = ops._CAPI_compute_frontier_heat_with_bias(seeds, indptr, indices, probs,
+                                                                      seeds_heat, num_picks, 0)
+        sampling_heat += seeds_heat
+        seeds_heat += frontier_heat
+        seeds = torch.nonzero(seeds_heat > 0).squeeze(1).to(indices.dtype)
+    feature_heat = sampling_heat + frontier_heat
+    if mode == "uva":
+        for t in (indptr, indices, probs):
+            if t is not None:
+                ops._CAPI_tensor_unpin_memory(t)
+    return sampling_heat, feature_heat
 
 
 def get_cache_nids_by_degree(indptr, ratio, rank=0, world_size=1):

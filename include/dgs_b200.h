@@ -178,7 +178,7 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
 
 /* Whole mini-batch: num_layers hops (fan_out walked from the back, like the reference's
  * sampler.cc:20 and DGL), each hop sampled and relabelled: out_row / out_col are positions in
- * out_frontier[l], hop l+1's seeds are hop l's frontier.  3 kernels per hop + 1, all enqueued
+ * out_frontier[l], hop l+1's seeds are hop l's frontier.  One cooperative launch, all enqueued
  * with device-side counts; the caller reads counts_dev = {nnz_0, |frontier_0|, nnz_1, ...} (2 L
  * int64) once at the end.  Replaces P2PCacheNodeClassificationSample{Uniform,Bias}
  * (src/sampling/sampler.cc:14-62).  fan_out[i] >= 0 here.

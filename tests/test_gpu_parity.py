@@ -710,6 +710,29 @@ def test_frontier_heat_matches_oracle(dgs, cuda):
         assert np.allclose(t2n(got), exp, rtol=1e-4, atol=1e-5)
 
 
+def test_get_node_heat_reference_semantics(dgs, cuda):
+    """DistGNN.cache.get_node_heat restated with the oracle's heat kernel
+    (python/DistGNN/cache/cache_value.py:6-53)."""
+    from DistGNN.cache import get_node_heat
+    N = 2000
+    indptr, indices, probs = dgs_synth.make_csr(N, 40000, seed=8, weights=True, classes=6)
+    nodes = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:300]
+    for pr in (None, probs):
+        for mode in ("cuda", "uva"):
+            sh, fh = get_node_heat(indptr.clone(), indices.clone(), nodes, [5, 10], None if pr is None else pr.clone(), mode)
+            samp = np.zeros(N, np.float32)
+            seeds_heat = np.zeros(N, np.float32)
+            seeds_heat[t2n(nodes)] = 1
+            seeds = t2n(nodes)
+            for k in (10, 5):
+                fr = oracle.frontier_heat(seeds, t2n(indptr), t2n(indices), None if pr is None else t2n(pr), seeds_heat, k, 0)
+                samp += seeds_heat
+                seeds_heat = seeds_heat + fr
+                seeds = np.nonzero(seeds_heat > 0)[0]
+            assert np.allclose(t2n(sh), samp, rtol=1e-4, atol=1e-5)
+            assert np.allclose(t2n(fh), samp + fr, rtol=1e-4, atol=1e-5)
+
+
 def test_pin_memory_roundtrip(dgs, cuda):
     t = torch.arange(1000, dtype=torch.float32).reshape(100, 10).clone()
     assert not t.is_pinned()
