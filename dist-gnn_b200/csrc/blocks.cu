@@ -792,7 +792,16 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     if (sm > smem_max) smem_max = sm;
   }
   static const char *mode_env = getenv("DGS_BLOCKS_MODE");  // "multi" forces the 3-kernels-per-hop path
-  const bool want_coop = !(mode_env && strcmp(mode_env, "multi") == 0);
+  static int coop_supported = -1;
+  if (coop_supported < 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess)
+      v = 0;
+    cudaGetLastError();
+    coop_supported = v;
+  }
+  const bool want_coop = coop_supported == 1 && !(mode_env && strcmp(mode_env, "multi") == 0);
 
   // ---- cooperative single-launch path
   if (want_coop && all_tile && L <= 8) {

@@ -7,6 +7,9 @@ dev = torch.device("cuda", 0)
 N, E, D, dt = dgs_synth.SHAPES["products"]
 ip, ix, _ = dgs_synth.make_csr(N, E, device=dev)
 sampler = dgs.classes.CSRSampler(ip, ix)
-seeds = dgs_synth.seed_batches(N, 1024, 12, device=dev)
+B = int(os.environ.get("BATCH", "1024"))
+FAN = [int(x) for x in os.environ.get("FAN", "15,10,5").split(",")]
+seeds = dgs_synth.seed_batches(N, B, 12, device=dev)
 for i in range(12):
-    sampler._CAPI_sample_node_classifiction(seeds[i], [15, 10, 5])
+    out = sampler._CAPI_sample_node_classifiction(seeds[i], FAN)
+print("edges", sum(b[2].numel() for b in out), "frontier", out[-1][1].numel(), [b[0].numel() for b in out])
