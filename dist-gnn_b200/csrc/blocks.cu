@@ -151,7 +151,10 @@ __device__ __forceinline__ unsigned int rl_insert(RlSlot *table, uint64_t mask, 
 }
 
 // N independent inserts with all first-probe CAS operations in flight before any result is used
-// (a single rl_insert is a dependent CAS -> atomicMin chain of ~1 us).
+// (a single rl_insert is a dependent CAS -> atomicMin chain of ~1 us).  Measured alternative: a
+// plain 16-byte load per probe first and atomics only when they can change something (about half
+// of a hop's sampled ids are duplicates) - fewer atomics but two dependent round trips for every
+// first insert; slower overall on B200 (118 vs 103 us per batch), so not used.
 template <int N>
 __device__ __forceinline__ void rl_insert_batch(RlSlot *table, uint64_t mask, const long long (&key)[N],
                                                 const unsigned int (&item)[N], const bool (&ok)[N],
@@ -279,7 +282,7 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
 // whole-batch kernel (phases separated by grid barriers).  Data produced by other CTAs in an
 // earlier phase is read with ld.global.cg (L2), never through a possibly stale L1 line.
 constexpr int kPkSeeds = 128;  // seeds per pick tile (256 was slower on B200: 4 B2 rounds per tile)
-constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase
+constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase (8: no gain)
 constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
 
@@ -322,8 +325,17 @@ template <typename IdT, typename ET, int MODE>
 __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__restrict__ seeds,
                                                 int64_t S_ub, int64_t S, int k, uint64_t rng_key,
                                                 IdT *__restrict__ pad_col, const HopState &cur,
-                                                uint64_t cap_mask) {
+                                                uint64_t cap_mask,
+                                                unsigned long long *fine = nullptr) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
+  auto fstamp = [&](int slot) {
+    if (fine != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      fine[slot] = t;
+    }
+  };
+  fstamp(0);
   __shared__ const IdT *s_row[kPkSeeds];
   __shared__ const float *s_w[kPkSeeds];
   __shared__ int s_deg[kPkSeeds];
@@ -362,6 +374,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       s_cnt[tid] = cnt;
       cur.cnt[i] = cnt;
     }
+    if (tile == blockIdx.x) fstamp(1);
     if (MODE == kUniform) {
       // random words of Floyd's draws, computed by all threads (one Philox block = 4 draws)
       const int blocks_per_seed = (k + 3) >> 2;
@@ -405,6 +418,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       }
     }
     __syncthreads();
+    if (tile == blockIdx.x) fstamp(2);
     const int slots = ns * k;
     for (int base = tid; base < slots; base += kBkThreads * kPkBatch) {
       long long v[kPkBatch];
@@ -450,7 +464,9 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       atomicMin(&cur.table[seed_pos].first, (unsigned int)(i0 + tid));
       cur.pos_seed[i0 + tid] = (unsigned int)seed_pos;
     }
+    if (tile == blockIdx.x) fstamp(3);
   }
+  fstamp(4);
 }
 
 // Rank phase: CTA per 64 seeds - flags first occurrences among the seeds (A) and the sampled
@@ -721,7 +737,8 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     const long long pS_live = ldcg(ws.pending_S);
     const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
-                                   (IdT *)ws.pad_col, cur, a.cap_mask);
+                                   (IdT *)ws.pad_col, cur, a.cap_mask,
+                                   a.trace ? a.trace + 256 + 8 * l : nullptr);
     wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S));
     stamp();
     grid.sync();
@@ -858,6 +875,14 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
         fprintf(stderr, "[dgs coop trace us, grid %d] pick sync rank tail sync emit sync:", grid);
         for (int i = 1; i < 1 + 7 * L; ++i)
           fprintf(stderr, "%s%.1f", (i - 1) % 7 == 0 ? " | " : " ", (double)(h[i] - h[i - 1]) * 1e-3);
+        fprintf(stderr, "\n");
+        unsigned long long f[8 * 8];
+        cudaMemcpy(f, trace_dev + 256, sizeof(f), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[dgs coop pick detail us: A B1 B2 tail(other tiles)]");
+        for (int l = 0; l < L; ++l)
+          fprintf(stderr, " | %.1f %.1f %.1f %.1f", (double)(f[8 * l + 1] - f[8 * l]) * 1e-3,
+                  (double)(f[8 * l + 2] - f[8 * l + 1]) * 1e-3, (double)(f[8 * l + 3] - f[8 * l + 2]) * 1e-3,
+                  (double)(f[8 * l + 4] - f[8 * l + 3]) * 1e-3);
         fprintf(stderr, "\n");
       }
       return 0;
