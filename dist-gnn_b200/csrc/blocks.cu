@@ -185,25 +185,49 @@ __device__ __forceinline__ void rl_wipe(RlSlot *table, unsigned int pos) {
   *reinterpret_cast<int4 *>(&table[pos]) = make_int4(-1, -1, -1, -1);
 }
 
-// wipe every slot the given hop touched (idempotent; duplicates wipe the same slot twice)
+// Wipe every slot the given hop touched (idempotent; duplicates wipe the same slot twice).
 // busy_ctas: CTAs [0, busy_ctas) have sampling work of their own in this phase; when enough idle
-// CTAs exist the wipe is left to them alone (it then overlaps the sampling chains entirely).
-__device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k, int64_t busy_ctas = 0) {
+// CTAs exist and the wipe is small it is left to them alone (it then overlaps the sampling chains
+// entirely).  A hop that touched a large part of the table is wiped linearly instead (coalesced
+// 16-byte stores over the whole table beat millions of scattered ones).
+__device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k, int64_t busy_ctas,
+                                         int64_t cap) {
+  const int64_t items = S * (1 + (int64_t)k);
+  if (items == 0) return;
   int64_t vgrid = gridDim.x, vbid = blockIdx.x;
-  if (busy_ctas < (int64_t)gridDim.x && (int64_t)gridDim.x - busy_ctas >= 64) {
+  const int64_t idle = (int64_t)gridDim.x - busy_ctas;
+  if (idle >= 64 && items <= idle * blockDim.x * 8) {
     if ((int64_t)blockIdx.x < busy_ctas) return;
-    vgrid = (int64_t)gridDim.x - busy_ctas;
+    vgrid = idle;
     vbid = (int64_t)blockIdx.x - busy_ctas;
   }
   const int64_t stride = vgrid * blockDim.x;
   const int64_t tid = vbid * blockDim.x + threadIdx.x;
+  if (items * 8 > cap) {
+    int4 *t = reinterpret_cast<int4 *>(h.table);
+    const int4 e = make_int4(-1, -1, -1, -1);
+    for (int64_t i = tid; i < cap; i += stride) t[i] = e;
+    return;
+  }
   for (int64_t i = tid; i < S; i += stride) rl_wipe(h.table, __ldcg(h.pos_seed + i));
   if (k > 0) {
     const int64_t E = S * k;
-    for (int64_t e = tid; e < E; e += stride) {
-      const int64_t i = e / k;
-      const int j = (int)(e - i * k);
-      if (j < __ldcg(h.cnt + i)) rl_wipe(h.table, __ldcg(h.pos_col + e));
+    for (int64_t e0 = tid; e0 < E; e0 += 4 * stride) {
+      unsigned int p[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {   // 4 independent (count, slot) load pairs in flight
+        const int64_t e = e0 + u * stride;
+        ok[u] = false;
+        if (e < E) {
+          const int64_t i = e / k;
+          ok[u] = (int)(e - i * k) < __ldcg(h.cnt + i);
+          p[u] = __ldcg(h.pos_col + e);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) rl_wipe(h.table, p[u]);
     }
   }
 }
@@ -272,7 +296,7 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
                                         w_idx, w_key, emit);
   }
   // wipe the other table: the slots the previous hop touched
-  if (prev.table != nullptr) wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k);
+  if (prev.table != nullptr) wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, gridDim.x, (int64_t)cap_mask + 1);
 }
 
 
@@ -665,7 +689,8 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
   const long long pS_live = *prev_S_dev;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
   pick_tile_phase<IdT, ET, MODE>(g, seeds, S_ub, S, k, rng_key, pad_col, cur, cap_mask);
-  wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S));
+  wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
+           (int64_t)cap_mask + 1);
 }
 
 __global__ void __launch_bounds__(kBkThreads)
@@ -739,7 +764,8 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
                                    (IdT *)ws.pad_col, cur, a.cap_mask,
                                    a.trace ? a.trace + 256 + 8 * l : nullptr);
-    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S));
+    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
+             (int64_t)a.cap_mask + 1);
     stamp();
     grid.sync();
     stamp();

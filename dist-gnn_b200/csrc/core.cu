@@ -88,6 +88,12 @@ int dgs_enable_peer_access(int peer_device) {
   return 0;
 }
 
+int dgs_set_l2_fetch_granularity(int bytes) {
+  DGS_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, "L2 fetch granularity must be 32, 64 or 128");
+  DGS_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return 0;
+}
+
 int dgs_host_unregister(void *host_ptr) {
   DGS_REQUIRE(host_ptr != nullptr, "dgs_host_unregister: null pointer");
   cudaError_t e = cudaHostUnregister(host_ptr);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "dgs_host_register": (C.c_int, [c_vp, C.c_size_t]),
     "dgs_host_unregister": (C.c_int, [c_vp]),
     "dgs_enable_peer_access": (C.c_int, [C.c_int]),
+    "dgs_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "dgs_nccl_get_unique_id": (C.c_int, [c_i64p]),
     "dgs_nccl_set": (C.c_int, [C.c_int, c_i64p, C.c_int]),
     "dgs_nccl_rank": (C.c_int, []),

@@ -50,6 +50,10 @@ void dgs_seed(uint64_t seed);
  * replaces TensorPinMemory / TensorUnpinMemory  (src/common/pin_memory.cc:7-19). */
 int dgs_host_register(void *host_ptr, size_t nbytes);
 int dgs_host_unregister(void *host_ptr);
+/* cudaLimitMaxL2FetchGranularity of the current device (32 / 64 / 128 bytes): random row gathers
+ * could over-fetch less with 32 (tuning knob; device-wide, never set implicitly; measured on B200:
+ * no effect on the gather, tools/l2_granularity_probe.py). */
+int dgs_set_l2_fetch_granularity(int bytes);
 /* single-process multi-GPU use (tests / probes): let kernels on the current device dereference
  * memory of peer_device (cudaDeviceEnablePeerAccess). */
 int dgs_enable_peer_access(int peer_device);
