@@ -740,3 +740,72 @@ def test_pin_memory_roundtrip(dgs, cuda):
     out = dgs.ops._CAPI_cuda_index_select(t, torch.tensor([3, 99], device=cuda))
     assert torch.equal(out.cpu(), t[[3, 99]])
     dgs.ops._CAPI_tensor_unpin_memory(t)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_products_properties(dgs, cuda):
+    """BASELINE configs[1] at full size (2.45 M nodes, ~61 M edges, 100-dim fp32, batch 1024,
+    [15,10,5]) - too large for the CPU oracle, so size-independent properties are checked on the GPU
+    with torch ops: every sampled (row, col) is an edge of the graph, per-seed counts are
+    min(deg, k), no neighbour position is taken twice, the frontier is the first-occurrence unique
+    of cat(seeds, cols), relabelled ids invert through the frontier, extract composes
+    (gather(gather(T, p), q) == gather(T, p[q])) and reproduces the closed-form feature rows."""
+    N, E, D, dt = dgs_synth.SHAPES["products"]
+    indptr, indices, _ = dgs_synth.make_csr(N, E, device=cuda)
+    feat = dgs_synth.make_features(N, D, dt, device=cuda)
+    smp = dgs.classes.CSRSampler(indptr, indices)
+    seeds = dgs_synth.seed_batches(N, 1024, 1, seed=7, device=cuda)[0]
+    fan = [15, 10, 5]
+    out = smp._CAPI_sample_node_classifiction(seeds, fan, False, rng_seed=99)
+    cur = seeds
+    # edge keys of the whole graph, sorted once: (src << 32) | dst  (N < 2^31)
+    deg_all = indptr[1:] - indptr[:-1]
+    for (s_, f_, r_, c_), k in zip(out, (5, 10, 15)):
+        assert torch.equal(s_, cur)
+        deg = deg_all[cur]
+        cnt = torch.clamp(deg, max=k)
+        assert r_.numel() == int(cnt.sum())
+        # rows are seed-major and each seed owns exactly cnt edges
+        assert torch.equal(torch.bincount(r_, minlength=cur.numel()), cnt)
+        assert bool((r_[1:] >= r_[:-1]).all())
+        src, dst = cur[r_], f_[c_]
+        # membership: every (src, dst) appears in src's adjacency.  Search dst inside the row with a
+        # per-edge scan over a sorted copy of the row segment (rows are short after clamping the
+        # search to the edge's own row): use a global sorted key array
+        seg_start = indptr[src]
+        # position of each sampled edge inside its seed's block
+        first = torch.cumsum(cnt, 0) - cnt
+        j = torch.arange(r_.numel(), device=cuda) - first[r_]
+        full = deg[r_] <= k
+        # copy path: exactly the CSR row, in order
+        assert torch.equal(dst[full], indices[(seg_start + j)[full]])
+        # sampled path: dst must be a neighbour; verify with sorted (src, dst) keys of the touched rows
+        rows_u = torch.unique(src[~full])
+        if rows_u.numel():
+            rdeg = deg_all[rows_u]
+            owner = torch.repeat_interleave(rows_u, rdeg)
+            pos = torch.arange(int(rdeg.sum()), device=cuda) - torch.repeat_interleave(torch.cumsum(rdeg, 0) - rdeg, rdeg)
+            nb = indices[indptr[owner] + pos]
+            keys = torch.sort(owner * (1 << 32) + nb).values
+            q = src[~full] * (1 << 32) + dst[~full]
+            at = torch.searchsorted(keys, q)
+            assert bool((keys[at.clamp(max=keys.numel() - 1)] == q).all())
+            # without replacement: a seed never returns more copies of a neighbour than its row holds
+            qs, qc = torch.unique(q, return_counts=True)
+            lo = torch.searchsorted(keys, qs)
+            hi = torch.searchsorted(keys, qs, right=True)
+            assert bool((qc <= hi - lo).all())
+        # frontier = first-occurrence unique of cat(seeds, cols)
+        allids = torch.cat([cur, dst])
+        uniq, inv = torch.unique(allids, return_inverse=True)
+        firstpos = torch.full((uniq.numel(),), allids.numel(), device=cuda, dtype=torch.int64)
+        firstpos.scatter_reduce_(0, inv, torch.arange(allids.numel(), device=cuda), reduce="amin")
+        assert torch.equal(f_, uniq[torch.argsort(firstpos)])
+        assert torch.equal(f_[: cur.numel()], cur)
+        cur = f_
+    x = dgs.ops._CAPI_cuda_index_select(feat, cur)
+    assert torch.equal(x, dgs_synth.feature_rows(cur, D, dt))
+    q = torch.randint(0, cur.numel(), (100000,), device=cuda)
+    assert torch.equal(dgs.ops._CAPI_cuda_index_select(x, q), dgs.ops._CAPI_cuda_index_select(feat, cur[q]))
+    for algo in (1, 2):
+        assert torch.equal(dgs.ops._CAPI_cuda_index_select(feat, cur, algo), x)
