@@ -27,6 +27,7 @@ struct RowSource {
   uint64_t cap_mask;
   PtrTable shards;
   int mod_world;  // > 0: row n lives in shard n % mod_world at slot n / mod_world (no table)
+  const long long *n_dev;  // optional live row count on the device (the kernel's n is then a bound)
 };
 
 template <typename IdT>
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kGatherThreads)
 gather_rows_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64_t row_bytes,
                    uint32_t vpr /* vectors per row */, uint32_t vpr_magic, char *__restrict__ out) {
   __shared__ const char *s_src[kGatherRows];
+  if (src.n_dev != nullptr) n = min(n, (int64_t)*src.n_dev);
   const int64_t num_tiles = (n + kGatherRows - 1) / kGatherRows;
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kGatherRows;
@@ -176,6 +178,7 @@ gather_rows_tma_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, i
   }
   __syncwarp();
 
+  if (src.n_dev != nullptr) n = min(n, (int64_t)*src.n_dev);
   const int64_t num_tiles = (n + kTmaRows - 1) / kTmaRows;
   // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   int64_t issue_tile = blockIdx.x;   // next tile to issue loads for
@@ -362,6 +365,46 @@ extern "C" int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_byt
   }
   DGS_ITYPE_SWITCH(itype, IdT, {
     return launch_gather<IdT>(src, (const IdT *)nids, n, row_bytes, (char *)out, algo, al,
+                              (cudaStream_t)stream);
+  });
+  return 0;
+}
+
+// Gather whose live row count is only known on the device (n_dev): lets the extract of a mini-batch
+// be enqueued right behind the sampling kernel, before the host has read the frontier size
+// (whole-batch pipeline).  n_ub bounds the grid and the output capacity.  Source:
+// feat == NULL -> plain table; feat + mod_world > 0 -> modulo shards; feat + loc_table -> hash.
+extern "C" int dgs_extract_dyn(const void *table, const dgs_p2p_server_t *feat, const void *loc_table,
+                               int64_t capacity, int mod_world, int64_t row_bytes, int itype,
+                               const void *nids, int64_t n_ub, const int64_t *n_dev, void *out,
+                               int algo, void *stream) {
+  DGS_REQUIRE(n_ub >= 0 && row_bytes > 0, "dgs_extract_dyn: bad sizes");
+  if (n_ub == 0) return 0;
+  DGS_REQUIRE(nids && out, "dgs_extract_dyn: null pointer");
+  RowSource src;
+  memset(&src, 0, sizeof(src));
+  src.table = (const char *)table;
+  src.n_dev = (const long long *)n_dev;
+  bool al = aligned16(out) && (table == nullptr || aligned16(table));
+  if (feat != nullptr) {
+    for (int d = 0; d < feat->world; ++d) {
+      src.shards.p[d] = feat->ptrs[d];
+      al = al && aligned16(feat->ptrs[d]);
+    }
+    if (mod_world > 0) {
+      DGS_REQUIRE(mod_world == feat->world, "dgs_extract_dyn: mod_world must equal the p2p world size");
+      src.mod_world = mod_world;
+    } else {
+      DGS_REQUIRE(loc_table && capacity > 0 && (capacity & (capacity - 1)) == 0,
+                  "dgs_extract_dyn: cached source needs a location table with power-of-two capacity");
+      src.loc = (const LocSlot *)loc_table;
+      src.cap_mask = (uint64_t)capacity - 1;
+    }
+  } else {
+    DGS_REQUIRE(table != nullptr, "dgs_extract_dyn: null table");
+  }
+  DGS_ITYPE_SWITCH(itype, IdT, {
+    return launch_gather<IdT>(src, (const IdT *)nids, n_ub, row_bytes, (char *)out, algo, al,
                               (cudaStream_t)stream);
   });
   return 0;

@@ -5,8 +5,8 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._util import (ID_DTYPES, check_cpu, check_cuda, contiguous, itype, ptr, stream,
-                    tensor_from_ptr, zero_ws)
+from ._util import (ID_DTYPES, check_cpu, check_cuda, check_device_readable, contiguous, itype, ptr,
+                    stream, tensor_from_ptr, zero_ws)
 
 lib = _lib.lib
 check = _lib.check
@@ -610,3 +610,105 @@ class P2PCacheFeatureServer:
 
     def close(self, barrier=True):
         self.gpu_features_.close(barrier)
+
+
+class BatchLoader:
+    """Extension (the whole-batch pipeline; no reference counterpart): one call per
+    mini-batch = seeds (host or device) -> multi-hop blocks + input features (+ labels), with every
+    kernel enqueued back to back and ONE host round trip.  The reference's training loop
+    (example/graphsage/node_classification.py:219-230) makes three plugin calls with a host sync
+    after sampling; here the extract reads the frontier size from device memory, so it starts the
+    moment the sampling kernel ends.
+
+      loader = BatchLoader(sampler, features, labels)       # sampler: CSRSampler / P2PCacheSampler
+      blocks, x, y = loader.load(seeds, [15, 10, 5])        # features: CUDA / pinned tensor or
+                                                            #           P2PCacheFeatureServer
+    Results are the same tensors the three separate calls return."""
+
+    def __init__(self, sampler, features, labels=None):
+        self._pipe = sampler._pipe
+        self._device = self._pipe._device
+        self._fs = features if isinstance(features, P2PCacheFeatureServer) else None
+        if self._fs is None:
+            check_device_readable(features, "features")
+            contiguous(features, "features")
+            self._table = features
+            stride = 1
+            for d in features.shape[1:]:
+                stride *= d
+            self._stride, self._dtype = stride, features.dtype
+            self._row_bytes = stride * features.element_size()
+            self._tail = tuple(features.shape[1:])
+        else:
+            self._stride, self._dtype, self._row_bytes = self._fs._stride, self._fs._dtype, self._fs._row_bytes
+            self._tail = (self._stride,)
+        self._labels = labels
+        if labels is not None:
+            check_device_readable(labels, "labels")
+
+    def load(self, seeds, fan_out, replace=False, rng_seed=None, algo=0, labels_out=None):
+        """-> (blocks, features of blocks[-1][1], labels of seeds or None).  `labels_out` (pinned host
+        tensor) additionally receives the labels inside the same host round trip."""
+        l = lib()
+        fan_out = [int(k) for k in fan_out]
+        L = len(fan_out)
+        if L == 0 or any(k < 0 for k in fan_out):
+            raise RuntimeError("BatchLoader needs fan-outs >= 0 (use the plugin calls for -1)")
+        with _on_device(self._device):
+            if not seeds.is_cuda:
+                seeds = seeds.to(self._device, non_blocking=True)     # pinned host -> device
+            seeds = seeds.contiguous()
+            if rng_seed is None:
+                rng_seed = l.dgs_randn_uint64()
+            pl = self._pipe._plan(seeds.numel(), fan_out)
+            if pl["ws"] is None or seeds.numel() == 0:
+                raise RuntimeError("BatchLoader: batch too large for the fused path")
+            arena = self._pipe.enqueue_only(seeds, fan_out, replace, rng_seed)   # no host sync
+            es, base = pl["es"], arena.data_ptr()
+            counts_ptr = base + pl["total"] * es
+            n_max = pl["ubs"][-1] + pl["nnz_ubs"][-1]
+            # output rows: the worst case the first time, then 1.25x the largest frontier seen for
+            # this (batch, fan-out) - a batch that overflows is re-extracted exactly (rare)
+            seen = pl.get("front_seen", 0)
+            n_ub = n_max if seen == 0 else min(n_max, seen + seen // 4 + 1024)
+            front_ptr = base + pl["offs"][-1][0] * es
+            x = torch.empty((n_ub,) + self._tail, dtype=self._dtype, device=self._device)
+            it = ID_DTYPES[seeds.dtype]
+            nf_dev = counts_ptr + 8 * (2 * L - 1)
+            if self._fs is None:
+                check(l.dgs_extract_dyn(ptr(self._table), None, None, 0, 0, self._row_bytes, it, front_ptr,
+                                        n_ub, nf_dev, ptr(x), int(algo), stream()), "BatchLoader extract")
+            else:
+                fs = self._fs
+                check(l.dgs_extract_dyn(fs._host_ptr, fs.gpu_features_._handle,
+                                        ptr(fs._table) if fs._table is not None else None, fs._cap,
+                                        fs._mod_world, self._row_bytes, it, front_ptr, n_ub, nf_dev,
+                                        ptr(x), int(algo), stream()), "BatchLoader extract")
+            y = ops._CAPI_cuda_index_select(self._labels, seeds) if self._labels is not None else None
+            if labels_out is not None and y is not None:
+                labels_out.copy_(y, non_blocking=True)
+            # the one host round trip: hop sizes -> pinned memory
+            pl["counts_host"].copy_(arena[pl["total"]:].view(torch.int64), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            counts = pl["counts_np"].tolist()
+            sizes = []
+            for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
+                nnz, nf = counts[2 * li], counts[2 * li + 1]
+                sizes += [nf, u + n - nf, nnz, n - nnz, nnz, n - nnz]
+            sizes.append(pl["pad"] + pl["count_slots"])
+            parts = arena.split_with_sizes(sizes)
+            nf = counts[2 * L - 1]
+            pl["front_seen"] = max(seen, nf)
+            if nf > n_ub:       # the adaptive bound was too small for this batch
+                x = (ops._CAPI_cuda_index_select(self._table, parts[6 * (L - 1)], algo)
+                     if self._fs is None else self._fs._CAPI_get_feature(parts[6 * (L - 1)], algo))
+            else:
+                x = x[:nf]
+        blocks = []
+        cur = seeds
+        for li in range(L):
+            frontier = parts[6 * li]
+            blocks.append((cur, frontier, parts[6 * li + 2], parts[6 * li + 4]))
+            cur = frontier
+        return blocks, x, y
+

@@ -127,6 +127,15 @@ int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_table, int64_
 int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_bytes, int itype,
                         const void *nids, int64_t n, void *out, int algo, void *stream);
 
+/* gather with a device-side row count (extension): n_dev (device int64) holds the live
+ * number of rows, n_ub bounds the grid and the capacity of `out` - the extract of a mini-batch can
+ * be enqueued right behind dgs_sample_blocks, before the host knows the frontier size.
+ * feat == NULL: plain table; feat + mod_world > 0: modulo shards; feat + loc_table: hash cache
+ * (table is then the pinned-host fallback). */
+int dgs_extract_dyn(const void *table, const dgs_p2p_server_t *feat, const void *loc_table,
+                    int64_t capacity, int mod_world, int64_t row_bytes, int itype, const void *nids,
+                    int64_t n_ub, const int64_t *n_dev, void *out, int algo, void *stream);
+
 /* ------------------------------------------------------------------ sub-CSR extraction
  * replaces ExtractIndptr / ExtractEdgeData (src/sampling/cuda/utils.cu:12-101).
  * indptr / edge_data may be device or mapped host memory. */

@@ -158,6 +158,15 @@ def main():
     assert fsm._mod_world == world
     for algo in (0, 1, 2):
         assert torch.equal(fsm._CAPI_get_feature(q, algo).cpu(), feat[q.cpu()])
+    # one-call loader over the sharded sampler + feature server == the separate plugin calls
+    smp = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, None, nids, N, rank)
+    loader = dgs.classes.BatchLoader(smp, fsm)
+    for it in range(3):
+        blocks, x, y = loader.load(seeds.cpu().pin_memory(), [10, 5], False, rng_seed=50 + it)
+        ref = smp._CAPI_sample_node_classifiction(seeds, [10, 5], False, rng_seed=50 + it)
+        assert all(torch.equal(a, b) for u, v in zip(blocks, ref) for a, b in zip(u, v))
+        assert y is None and torch.equal(x.cpu(), feat[ref[-1][1].cpu()])
+    smp.close()
     dist.barrier()
     fsm.close()
     print(f"RANK {rank} OK", flush=True)

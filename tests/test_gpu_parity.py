@@ -681,6 +681,56 @@ def test_from_device_shard_with_hash_table(dgs, cuda):
     assert torch.equal(fs._CAPI_get_feature(q).cpu(), feat[q.cpu()])
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("source", ["cuda", "pinned", "server_mod", "server_hash"])
+def test_batch_loader_equals_separate_calls(dgs, cuda, idt, source):
+    """BatchLoader (one enqueue, device-side frontier count) == sample + extract + label gather
+    made as three plugin calls with the same RNG seed; covers the adaptive output bound (incl. a
+    batch that overflows it) and pinned-host seeds."""
+    N, D = 6000, 100
+    indptr, indices, _ = dgs_synth.make_csr(N, 120000, seed=44, classes=6, id_dtype=idt)
+    feat = dgs_synth.feature_rows(torch.arange(N), D)
+    labels = (torch.arange(N) % 47).to(cuda)
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda))
+    if source == "cuda":
+        src = feat.to(cuda)
+        ext = lambda q: dgs.ops._CAPI_cuda_index_select(src, q)
+    elif source == "pinned":
+        src = feat.pin_memory()
+        ext = lambda q: dgs.ops._CAPI_cuda_index_select(src, q)
+    elif source == "server_mod":
+        src = dgs.classes.P2PCacheFeatureServer(feat.pin_memory(), torch.arange(N), 0)
+        assert src._mod_world == 1
+        ext = src._CAPI_get_feature
+    else:
+        cache = torch.randperm(N, generator=torch.Generator().manual_seed(5))[:2000]
+        src = dgs.classes.P2PCacheFeatureServer(feat.pin_memory(), cache, 0)
+        assert src._mod_world == 0
+        ext = src._CAPI_get_feature
+    loader = dgs.classes.BatchLoader(smp, src, labels)
+    g = torch.Generator().manual_seed(8)
+    lab_host = torch.empty(64, dtype=torch.int64).pin_memory()
+    # batch sizes: small first (tight adaptive bound), then seeds of high degree to overflow it
+    deg = indptr[1:] - indptr[:-1]
+    order = torch.argsort(deg)
+    batches = [order[:64], order[-64:], torch.randperm(N, generator=g)[:64], order[-64:]]
+    for bi, sd in enumerate(batches):
+        sd = sd.to(idt)
+        seeds = sd.pin_memory() if bi % 2 else sd.to(cuda)
+        blocks, x, y = loader.load(seeds, [10, 5], False, rng_seed=100 + bi, labels_out=lab_host)
+        ref = smp._CAPI_sample_node_classifiction(sd.to(cuda), [10, 5], False, rng_seed=100 + bi)
+        assert len(blocks) == len(ref)
+        for a, b in zip(blocks, ref):
+            for u, v in zip(a, b):
+                assert torch.equal(u, v)
+        fr = ref[-1][1]
+        assert x.shape == (fr.numel(), D)
+        assert torch.equal(x, ext(fr)) and torch.equal(x.cpu(), feat[fr.cpu().long()])
+        assert torch.equal(y, labels[sd.to(cuda).long()]) and torch.equal(lab_host, y.cpu())
+    with pytest.raises(RuntimeError):
+        loader.load(batches[0].to(idt).to(cuda), [-1, 5])
+
+
 def test_p2p_server_single_rank(dgs, cuda):
     t = torch.arange(24, dtype=torch.float32, device=cuda).reshape(6, 4)
     srv = dgs.classes.TensorP2PServer(t)

@@ -33,6 +33,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--bias", action="store_true")
     ap.add_argument("--extract-rows", type=int, default=1_000_000)
+    ap.add_argument("--replicate-hot", type=float, default=0.0,
+                    help="also cache the feature rows of the top FRAC nodes by degree on EVERY GPU "
+                         "(the reference's hot-node cache idea): local hits replace NVLink reads; the "
+                         "location map is then the hash table (local copy wins)")
     args = ap.parse_args()
     fan = [int(x) for x in args.fan_out.split(",")]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -48,7 +52,18 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     smp = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, spr, nids, N, rank)
-    fs = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat, nids, N, rank)
+    hot_extra = 0
+    if args.replicate_hot > 0 and world > 1:
+        deg = dgs_synth.degrees(N, E, device=dev)
+        hot = torch.topk(deg, int(N * args.replicate_hot)).indices
+        del deg
+        extra = hot[hot % world != rank]                 # hot nodes this rank does not own
+        hot_extra = extra.numel()
+        feat = torch.cat([feat, dgs_synth.make_features(N, D, dt, device=dev, nids=extra)])
+        fnids = torch.cat([nids, extra.to(nids.dtype)])
+        fs = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat, fnids, N, rank)
+    else:
+        fs = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat, nids, N, rank)
     del sp, si, spr, feat
     torch.cuda.empty_cache()
     t_build = time.time() - t0 - t_gen
@@ -145,7 +160,8 @@ def main():
         R = args.extract_rows
         print(json.dumps({
             "shape": args.shape, "n_gpus": world, "batch": args.batch, "fan_out": fan,
-            "bias": args.bias, "gen_s": t_gen, "build_s": t_build,
+            "bias": args.bias, "replicate_hot": args.replicate_hot, "hot_rows_replicated_per_gpu": hot_extra,
+            "loc_mode": "modulo" if fs._mod_world else "hash", "gen_s": t_gen, "build_s": t_build,
             "ms_per_step": ms / args.steps, "batches_per_sec": world * args.steps / (ms * 1e-3),
             "sampled_edges_per_sec": tot_edges / (ms * 1e-3),
             "extract_gbps_in_step": tot_rows * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
