@@ -234,3 +234,39 @@ extern "C" int dgs_frontier_heat(int itype, int etype, const void *seeds, int64_
   });
   return 0;
 }
+
+// ------------------------------------------------------------------ block construction
+// The sampled COO of a hop leaves dgs_sample_blocks / dgs_sample_neighbors sorted by destination
+// (coo_row ascending: seed i owns one contiguous run), so the CSC a message-passing layer wants -
+// what dgl.create_block((coo_col, coo_row)) builds lazily in the caller
+// (example/graphsage/node_classification.py:18-28) - is just the run boundaries:
+// indptr[r] = first edge whose row is >= r.  Thread e closes the runs that end at edge e.
+template <typename IdT>
+__global__ void __launch_bounds__(256) row_runs_to_indptr_kernel(const IdT *__restrict__ row, int64_t nnz,
+                                                                 int64_t num_rows,
+                                                                 IdT *__restrict__ indptr,
+                                                                 int *__restrict__ unsorted) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e <= nnz;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = e == 0 ? -1 : (int64_t)row[e - 1];
+    int64_t hi = e == nnz ? num_rows : (int64_t)row[e];
+    if (hi < lo || hi > num_rows || (e < nnz && hi == num_rows)) {
+      if (unsorted) *unsorted = 1;
+      continue;
+    }
+    for (int64_t r = lo + 1; r <= hi; ++r) indptr[r] = (IdT)e;
+  }
+}
+
+extern "C" int dgs_coo_rows_to_indptr(int itype, const void *sorted_rows, int64_t nnz, int64_t num_rows,
+                                      void *indptr, int *unsorted_flag_dev, void *stream) {
+  DGS_REQUIRE(nnz >= 0 && num_rows >= 0 && indptr, "dgs_coo_rows_to_indptr: bad argument");
+  DGS_REQUIRE(nnz == 0 || sorted_rows, "dgs_coo_rows_to_indptr: null rows");
+  int grid = grid_for(nnz + 1, 256, 8);
+  DGS_ITYPE_SWITCH(itype, IdT, {
+    row_runs_to_indptr_kernel<IdT><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const IdT *)sorted_rows, nnz, num_rows, (IdT *)indptr, unsorted_flag_dev);
+    DGS_LAUNCH_CHECK();
+  });
+  return 0;
+}

@@ -69,6 +69,7 @@ SIGNATURES = {
     "dgs_extract_sharded": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "dgs_extract_dyn": (C.c_int, [c_vp, c_vp, c_vp, c_i64, C.c_int, c_i64, C.c_int, c_vp, c_i64, c_vp,
                                   c_vp, C.c_int, c_vp]),
+    "dgs_coo_rows_to_indptr": (C.c_int, [C.c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dgs_extract_indptr_ws_bytes": (c_i64, [c_i64]),
     "dgs_extract_indptr": (C.c_int, [C.c_int, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dgs_extract_edge_data": (C.c_int, [C.c_int, C.c_int, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp,

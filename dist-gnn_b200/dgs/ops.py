@@ -303,3 +303,21 @@ def _CAPI_compute_frontier_heat_with_bias(seeds, indptr, indices, probs, seeds_h
     processed (the reference skips the last one, :107 - a bug we do not replicate)."""
     check_device_readable(probs, "probs")
     return _heat(seeds, indptr, indices, probs, seeds_heat, num_picks, indptr_diff)
+
+
+# ------------------------------------------------------------------ block construction (extension)
+def coo_rows_to_indptr(coo_row, num_rows, check_sorted=False):
+    """CSC row pointer (num_rows + 1 entries, id dtype) of a sampled hop whose `coo_row` is ascending
+    - which every sampling op here guarantees.  Replaces what dgl.create_block derives in the caller
+    (example/graphsage/node_classification.py:18-28).  check_sorted=True verifies the precondition
+    (one host sync) and raises if it does not hold."""
+    check_cuda(coo_row, "coo_row")
+    coo_row = coo_row.contiguous()
+    indptr = torch.empty(int(num_rows) + 1, dtype=coo_row.dtype, device=coo_row.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=coo_row.device) if check_sorted else None
+    check(lib().dgs_coo_rows_to_indptr(itype(coo_row, "coo_row"), ptr(coo_row), coo_row.numel(),
+                                       int(num_rows), ptr(indptr), ptr(flag) if check_sorted else None,
+                                       stream()), "coo_rows_to_indptr")
+    if check_sorted and int(flag.item()):
+        raise RuntimeError("coo_rows_to_indptr: rows are not ascending in [0, num_rows)")
+    return indptr

@@ -241,6 +241,15 @@ int dgs_frontier_heat(int itype, int etype, const void *seeds, int64_t n, const 
                       const void *indices, const float *probs, const float *seeds_heat,
                       float *frontier_heat, int64_t num_picks, int64_t indptr_diff, void *stream);
 
+/* ------------------------------------------------------------------ block construction
+ * CSC row pointer of a sampled hop: replaces what dgl.create_block((coo_col, coo_row), ...) derives
+ * in the caller (example/graphsage/node_classification.py:18-28).  `sorted_rows` = the hop's coo_row
+ * (ascending - every sampling entry point emits it so); indptr gets num_rows + 1 entries of the id
+ * type.  *unsorted_flag_dev (optional, zeroed by the caller) is set to 1 if the rows are not
+ * ascending or out of range. */
+int dgs_coo_rows_to_indptr(int itype, const void *sorted_rows, int64_t nnz, int64_t num_rows,
+                           void *indptr, int *unsorted_flag_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -731,6 +731,40 @@ def test_batch_loader_equals_separate_calls(dgs, cuda, idt, source):
         loader.load(batches[0].to(idt).to(cuda), [-1, 5])
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+def test_build_blocks_csc(dgs, cuda, idt):
+    """DistGNN.dataloading.build_blocks: coo_row of every hop is ascending, the CSC row pointer equals
+    searchsorted, blocks come input-side first with the caller's srcdata / dstdata ids."""
+    from DistGNN.dataloading import NID, build_blocks
+    N = 5000
+    indptr, indices, _ = dgs_synth.make_csr(N, 80000, seed=23, classes=6, id_dtype=idt)
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda))
+    seeds = torch.randperm(N, generator=torch.Generator().manual_seed(2))[:300].to(idt).to(cuda)
+    batch = smp._CAPI_sample_node_classifiction(seeds, [10, 5, 3], False, rng_seed=4)
+    blocks = build_blocks(batch)
+    assert len(blocks) == 3 and torch.equal(blocks[-1].dstdata[NID], seeds)
+    for blk, (sd, fr, row, col) in zip(blocks, reversed(batch)):
+        ip, src, eid = blk.csc()
+        r = t2n(row)
+        assert np.all(np.diff(r) >= 0)
+        assert ip.dtype == idt and np.array_equal(t2n(ip), np.searchsorted(r, np.arange(sd.numel() + 1)))
+        assert torch.equal(src, col) and torch.equal(eid.cpu(), torch.arange(row.numel(), dtype=idt))
+        assert blk.num_src_nodes() == fr.numel() and blk.num_dst_nodes() == sd.numel()
+        assert blk.num_edges() == row.numel() and torch.equal(blk.srcdata[NID], fr)
+        assert int(blk.in_degrees().sum()) == row.numel()
+    for a, b in zip(blocks[:-1], blocks[1:]):       # chained: dst of the outer hop = src of the next
+        assert torch.equal(a.dstdata[NID], b.srcdata[NID])
+    # rows with no edges at both ends, empty input, and the sortedness check
+    row = torch.tensor([2, 2, 5], dtype=idt, device=cuda)
+    assert dgs.ops.coo_rows_to_indptr(row, 8, check_sorted=True).tolist() == [0, 0, 0, 2, 2, 2, 3, 3, 3]
+    assert dgs.ops.coo_rows_to_indptr(row[:0], 3).tolist() == [0, 0, 0, 0]
+    assert dgs.ops.coo_rows_to_indptr(row[:0], 0).tolist() == [0]
+    with pytest.raises(RuntimeError, match="ascending"):
+        dgs.ops.coo_rows_to_indptr(torch.tensor([3, 1], dtype=idt, device=cuda), 4, check_sorted=True)
+    with pytest.raises(RuntimeError, match="ascending"):
+        dgs.ops.coo_rows_to_indptr(torch.tensor([1, 4], dtype=idt, device=cuda), 4, check_sorted=True)
+
+
 def test_p2p_server_single_rank(dgs, cuda):
     t = torch.arange(24, dtype=torch.float32, device=cuda).reshape(6, 4)
     srv = dgs.classes.TensorP2PServer(t)
