@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--fan-out", default="15,10,5")
     ap.add_argument("--bias", action="store_true")
     ap.add_argument("--extract-algo", type=int, default=0)
+    ap.add_argument("--layout", default="policy", choices=["policy", "sharded"],
+                    help="N > 1: where graph + feature rows live. policy = placement computed by "
+                         "DistGNN.cache (the reference's selfish / selfless / auto model) for the free "
+                         "HBM; sharded = node n on GPU n mod N, remote rows over NVLink")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,19 +228,45 @@ def run_b200(args, fan_out):
             return dgs.ops._CAPI_cuda_index_select(ft, nids, args.extract_algo)
         layout = "graph + features resident in HBM, un-cached path"
     else:
-        # shard: node n -> GPU n mod world.  The class API wants the whole graph as pinned CPU tensors
-        # (src/sampling/sampler.cc:64-86); the products shape is small enough for that.
-        cache = torch.arange(rank, N, world, dtype=torch.int64)
+        # The class API wants the whole graph as pinned CPU tensors (src/sampling/sampler.cc:64-86);
+        # the products shape is small enough for that.
         ipc, ixc, ftc = ip.cpu().pin_memory(), ix.cpu().pin_memory(), ft.cpu().pin_memory()
         prc = pr.cpu().pin_memory() if pr is not None else torch.Tensor()
         del ip, ix, ft
         torch.cuda.empty_cache()
-        sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, cache, rank)
-        fserver = dgs.classes.P2PCacheFeatureServer(ftc, cache, rank)
+        shard_nids = torch.arange(rank, N, world, dtype=torch.int64)   # node n -> GPU n mod world
+        policy = None
+        if args.layout == "policy":
+            # what the reference's training script does (example/graphsage/node_classification.py:
+            # 73-167): heat of every node -> value per byte -> knapsack over the free device memory
+            from DistGNN.cache import choose_cache_policy, get_available_memory, get_node_heat
+            graph = {"indptr": ipc, "indices": ixc, "features": ftc}
+            if pr is not None:
+                graph["probs"] = prc
+            sh, fh = get_node_heat(ipc, ixc, torch.arange(N), fan_out,
+                                   probs=prc if pr is not None else None, mode="uva")
+            free = get_available_memory(local_rank, 7 << 30)
+            name, s_nids, f_nids = choose_cache_policy(graph, sh, fh, free, world,
+                                                       probs="probs" if pr is not None else None)
+            del sh, fh
+            policy = {"chosen": name, "free_hbm_gb": free / 1e9,
+                      "structure_nodes_cached": int(s_nids.numel()),
+                      "feature_rows_cached": int(f_nids.numel())}
+            s_nids, f_nids = torch.sort(s_nids.cpu())[0], torch.sort(f_nids.cpu())[0]
+        else:
+            s_nids = f_nids = shard_nids
+        sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, s_nids, rank)
+        fserver = dgs.classes.P2PCacheFeatureServer(ftc, f_nids, rank)
 
         def extract(nids):
             return fserver._CAPI_get_feature(nids, args.extract_algo)
-        layout = f"CSR + features sharded nid mod {world} over {world} GPUs, NVLink peer loads in-kernel"
+        if sampler._mod_world < 0 and fserver._mod_world < 0:
+            layout = (f"placement by the cache policy ({policy['chosen']}): everything fits the free HBM, "
+                      f"so every GPU holds a full replica (CSR + features); no remote reads")
+        elif sampler._mod_world > 0:
+            layout = f"CSR + features sharded nid mod {world} over {world} GPUs, NVLink peer loads in-kernel"
+        else:
+            layout = f"placement by the cache policy ({policy['chosen']}), location table, NVLink peer loads"
 
     # distinct seed batches per rank and per step
     seeds_all = dgs_synth.seed_batches(N, args.batch, 3 * (K + W) + 2, seed=rank)
@@ -379,6 +409,49 @@ def run_b200(args, fan_out):
     fused_edges = sum_over_ranks(f_edges)
     clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through both timed regions
 
+    # ---- N > 1, policy placement: the same steps over the modulo-sharded layout as well (north star
+    # item 4: remote CSR rows and feature rows read by NVLink peer loads inside the kernels)
+    sharded = None
+    if world > 1 and args.layout == "policy":
+        sampler2 = dgs.classes.P2PCacheSampler(ipc, ixc, prc, shard_nids, rank)
+        fserver2 = dgs.classes.P2PCacheFeatureServer(ftc, shard_nids, rank)
+        for i in range(W + 2):
+            b2 = sampler2._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+            fserver2._CAPI_get_feature(b2[-1][1], args.extract_algo)
+        barrier()
+        s_edges = s_rows = 0
+        e0.record()
+        for i in range(W, W + K):
+            b2 = sampler2._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+            x2 = fserver2._CAPI_get_feature(b2[-1][1], args.extract_algo)
+            s_edges += sum(b[2].numel() for b in b2)
+            s_rows += x2.shape[0]
+        e1.record()
+        barrier()
+        ms2 = max_over_ranks(e0.elapsed_time(e1))
+        fr2 = [f.clone() for f in frontiers]
+        outs = [fserver2._CAPI_get_feature(f, args.extract_algo) for f in fr2]
+        del outs
+        barrier()
+        outs = []
+        x0.record()
+        for f in fr2:
+            outs.append(fserver2._CAPI_get_feature(f, args.extract_algo))
+        x1.record()
+        torch.cuda.synchronize()
+        ex2_ms = max_over_ranks(x0.elapsed_time(x1))
+        del outs
+        tot_e2, tot_r2 = sum_over_ranks(s_edges), sum_over_ranks(s_rows)
+        remote = sum(f.numel() for f in fr2) * row_bytes * (world - 1) / world
+        sharded = {"layout": f"CSR + features sharded nid mod {world}, NVLink peer loads in-kernel",
+                   "value": tot_e2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
+                   "batches_per_sec": world * K / (ms2 * 1e-3),
+                   "extract_avg_launch_ms": ex2_ms / K,
+                   "extract_peer_load_gbps_per_gpu": remote / (ex2_ms * 1e-3) / 1e9,
+                   "nvlink_peak_gbps": 900}
+        sampler2.close()
+        fserver2.close()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -428,6 +501,8 @@ def run_b200(args, fan_out):
                 "ms_per_step": ms_e2e / K, "batches_per_sec": world * K / (ms_e2e * 1e-3),
                 "note": "seeds from pinned host memory, blocks + features stay on the device (the "
                         "plugin API returns CUDA tensors), labels of the batch + hop sizes read back"},
+        "placement_policy": policy if world > 1 else None,
+        "sharded_layout": sharded,
         "e2e_fused": {"value": fused_edges / (ms_fused * 1e-3), "unit": UNIT,
                       "ms_per_step": ms_fused / K, "batches_per_sec": world * K / (ms_fused * 1e-3),
                       "note": "extension, not the reference-facing API: dgs.classes.BatchLoader enqueues "

@@ -32,10 +32,12 @@ def get_node_heat(indptr, indices, node_ids, fan_outs, probs=None, mode="uva", c
     if capi is None:
         import dgs as capi
     ops = capi.ops
+    pinned_here = []
     if mode == "uva":
         for t in (indptr, indices, probs):
-            if t is not None:
+            if t is not None and not t.is_pinned():    # already-pinned inputs are left alone
                 ops._CAPI_tensor_pin_memory(t)
+                pinned_here.append(t)
     else:
         indptr, indices = indptr.cuda(), indices.cuda()
         if probs is not None:
@@ -57,10 +59,9 @@ def get_node_heat(indptr, indices, node_ids, fan_outs, probs=None, mode="uva", c
         seeds_heat += frontier_heat
         seeds = torch.nonzero(seeds_heat > 0).squeeze(1).to(indices.dtype)
     feature_heat = sampling_heat + frontier_heat
-    if mode == "uva":
-        for t in (indptr, indices, probs):
-            if t is not None:
-                ops._CAPI_tensor_unpin_memory(t)
+    torch.cuda.current_stream().synchronize()
+    for t in pinned_here:
+        ops._CAPI_tensor_unpin_memory(t)
     return sampling_heat, feature_heat
 
 

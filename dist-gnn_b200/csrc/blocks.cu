@@ -93,7 +93,8 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
     ub += e;
   }
   int64_t cap = 64;
-  while (cap < 2 * items_max) cap <<= 1;
+  static const int cap_pct = getenv("DGS_RL_CAP_PCT") ? atoi(getenv("DGS_RL_CAP_PCT")) : 200;
+  while (cap * 100 < (int64_t)cap_pct * items_max) cap <<= 1;
   const int idb = itype == DGS_I64 ? 8 : 4;
   p->S_max = S_max;
   p->E_max = E_max;
@@ -739,6 +740,7 @@ struct BatchArgs {
   int L;
   uint64_t cap_mask;
   unsigned long long *trace;  // debug: %globaltimer stamps of CTA 0 around every phase
+  int wipe_first;
   HopArgs hop[8];
 };
 
@@ -761,11 +763,15 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     const HopState &prev = ws.hop[h.cur ^ 1];
     const long long pS_live = ldcg(ws.pending_S);
     const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
+    if (a.wipe_first)
+      wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
+               (int64_t)a.cap_mask + 1);
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
                                    (IdT *)ws.pad_col, cur, a.cap_mask,
                                    a.trace ? a.trace + 256 + 8 * l : nullptr);
-    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
-             (int64_t)a.cap_mask + 1);
+    if (!a.wipe_first)
+      wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
+               (int64_t)a.cap_mask + 1);
     stamp();
     grid.sync();
     stamp();
@@ -852,6 +858,8 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     memset(&a, 0, sizeof(a));
     a.L = L;
     a.cap_mask = cap_mask;
+    static const int wipe_first = getenv("DGS_WIPE_FIRST") ? atoi(getenv("DGS_WIPE_FIRST")) : 0;
+    a.wipe_first = wipe_first;
     for (int l = 0; l < L; ++l) {
       HopArgs &h = a.hop[l];
       const int pl = l > 0 ? l - 1 : L - 1;

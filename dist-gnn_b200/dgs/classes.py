@@ -102,6 +102,10 @@ class TensorP2PServer:
         self.rank = rank
         return self
 
+    @property
+    def _local_ptr(self):
+        return lib().dgs_p2p_server_ptr(self._handle, self.rank)
+
     # -- reference API
     def _CAPI_get_local_device_tensor(self):
         """GetLocalDeviceTensor (tensor_p2p_cache.cc:120-125): local shard, original shape."""
@@ -131,30 +135,43 @@ class TensorP2PServer:
             pass
 
 
-def _is_modulo_sharded(local_nids, num_nodes):
-    """True on every rank iff rank r caches exactly [r, r + P, r + 2 P, ...] in that order, i.e.
-    node n lives on GPU n % P at shard slot n // P.  Collective (one int64 all-gather)."""
+def _placement_mode(local_nids, num_nodes):
+    """How the ranks' cache sets tile the node ids - decided collectively (one int64 all-gather):
+      "modulo"  : rank r caches exactly [r, r + P, r + 2 P, ...] in that order: node n lives on
+                  GPU n % P at shard slot n // P;
+      "replica" : (P > 1) every rank caches every node in id order: node n is in the LOCAL shard at
+                  slot n (the reference resolves ties to the local copy too, hashmap.cu:37-42);
+      "hash"    : anything else."""
     l = lib()
     world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
-    want = (num_nodes - rank + world - 1) // world
     mine = 0
-    if local_nids.numel() == want:
+    if local_nids.numel() == (num_nodes - rank + world - 1) // world:
         exp = torch.arange(rank, num_nodes, world, dtype=local_nids.dtype, device=local_nids.device)
         mine = int(torch.equal(local_nids, exp))
+    if world > 1 and local_nids.numel() == num_nodes:
+        exp = torch.arange(num_nodes, dtype=local_nids.dtype, device=local_nids.device)
+        mine = 2 * int(torch.equal(local_nids, exp))
     flags = (C.c_int64 * world)()
-    check(l.dgs_nccl_allgather_i64(mine, flags), "modulo-sharding check")
-    return all(int(f) == 1 for f in flags)
+    check(l.dgs_nccl_allgather_i64(mine, flags), "cache placement check")
+    codes = {int(f) for f in flags}
+    return {(1,): "modulo", (2,): "replica"}.get(tuple(codes), "hash")
+
+
+def _is_modulo_sharded(local_nids, num_nodes):
+    return _placement_mode(local_nids, num_nodes) == "modulo"
 
 
 def _build_loc_table(local_nids, num_nodes, device, allow_modulo=True):
     """All-gather the per-rank cached id lists and build the packed location table
     (CreateNidsP2PCacheHashMapCUDA, src/hashmap/cuda/hashmap.cu:15-77).  Returns
-    (table int64[2*cap] or None, capacity, n_unique, mod_world).  When the cache sets are an exact
-    modulo sharding of all nodes the owner is arithmetic: no table is built (mod_world = P)."""
+    (table int64[2*cap] or None, capacity, n_unique, mod_world).  No table is built when the owner
+    is arithmetic: an exact modulo sharding of all nodes (mod_world = P) or a full replica on every
+    rank (mod_world = -1)."""
     l = lib()
     world, rank = l.dgs_nccl_world(), l.dgs_nccl_rank()
-    if allow_modulo and _is_modulo_sharded(local_nids, num_nodes):
-        return None, l.dgs_loc_table_capacity(num_nodes), num_nodes, world
+    mode = _placement_mode(local_nids, num_nodes) if allow_modulo else "hash"
+    if mode != "hash":
+        return None, l.dgs_loc_table_capacity(num_nodes), num_nodes, world if mode == "modulo" else -1
     table, cap, n_unique = _hash_loc_table(local_nids, num_nodes, device)
     return table, cap, n_unique, 0
 
@@ -428,6 +445,13 @@ class P2PCacheSampler:
             torch.cuda.current_stream().synchronize()
             _barrier()
         all_cached = self._n_unique >= num_nodes
+        if self._mod_world < 0:
+            # full replica: the local shards ARE the graph - same handle as an un-cached CSR in HBM
+            loc_pr = self.gpu_probs_._CAPI_get_local_device_tensor() if self.bias_ else None
+            self._graph = ops._make_graph(self.gpu_indptr_._CAPI_get_local_device_tensor(),
+                                          self.gpu_indices_._CAPI_get_local_device_tensor(), loc_pr)
+            self._pipe = _BlockPipeline(self._graph, self._device, sub_indices.dtype)
+            return
         g = _lib.Graph()
         g.itype = itype(sub_indices, "indices")
         g.etype = itype(sub_indptr, "indptr")
@@ -590,7 +614,11 @@ class P2PCacheFeatureServer:
         n = nids.numel()
         out = torch.empty((n, self._stride), dtype=self._dtype, device=nids.device)
         if n:
-            if self._mod_world > 0:
+            if self._mod_world < 0:    # full replica: plain gather from the local shard
+                check(lib().dgs_index_select(self.gpu_features_._local_ptr, self._row_bytes,
+                                             itype(nids, "nids"), ptr(nids), n, ptr(out), int(algo),
+                                             stream()), "_CAPI_get_feature")
+            elif self._mod_world > 0:
                 check(lib().dgs_extract_sharded(self.gpu_features_._handle, self._row_bytes,
                                                 itype(nids, "nids"), ptr(nids), n, ptr(out),
                                                 int(algo), stream()), "_CAPI_get_feature")
@@ -675,8 +703,9 @@ class BatchLoader:
             x = torch.empty((n_ub,) + self._tail, dtype=self._dtype, device=self._device)
             it = ID_DTYPES[seeds.dtype]
             nf_dev = counts_ptr + 8 * (2 * L - 1)
-            if self._fs is None:
-                check(l.dgs_extract_dyn(ptr(self._table), None, None, 0, 0, self._row_bytes, it, front_ptr,
+            if self._fs is None or self._fs._mod_world < 0:
+                table = ptr(self._table) if self._fs is None else self._fs.gpu_features_._local_ptr
+                check(l.dgs_extract_dyn(table, None, None, 0, 0, self._row_bytes, it, front_ptr,
                                         n_ub, nf_dev, ptr(x), int(algo), stream()), "BatchLoader extract")
             else:
                 fs = self._fs

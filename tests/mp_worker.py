@@ -169,6 +169,36 @@ def main():
     smp.close()
     dist.barrier()
     fsm.close()
+    # ---- full replica on every rank (what the cache policy yields when everything fits in HBM):
+    # no location table, every read is local; same results as the sharded layouts
+    everything = torch.arange(N)
+    for bias in (False, True):
+        smp = dgs.classes.P2PCacheSampler(ipp, ixp, prp if bias else torch.Tensor(), everything, rank)
+        assert smp._mod_world == -1 and smp._table is None
+        exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(ip), t2n(ix), 2)
+        for fan in ([-1, -1], [maxdeg, maxdeg]):
+            out = smp._CAPI_sample_node_classifiction(seeds, fan, False)
+            for a, e in zip(out, exp):
+                for x, z in zip(a, e):
+                    assert np.array_equal(t2n(x), z)
+        key, idx, devid = smp._CAPI_get_local_cache_hashmap_tensors()      # built on demand: local wins
+        live = key >= 0
+        assert int(live.sum()) == N and bool((devid[live] == rank).all())
+        assert torch.equal(idx[live], key[live])
+        smp.close()
+    fsr = dgs.classes.P2PCacheFeatureServer(fp, everything, rank)
+    assert fsr._mod_world == -1
+    for algo in (0, 1, 2):
+        assert torch.equal(fsr._CAPI_get_feature(q, algo).cpu(), feat[q.cpu()])
+    smp = dgs.classes.P2PCacheSampler(ipp, ixp, torch.Tensor(), everything, rank)
+    loader = dgs.classes.BatchLoader(smp, fsr)
+    blocks, x, _ = loader.load(seeds, [10, 5], False, rng_seed=77)
+    ref = smp._CAPI_sample_node_classifiction(seeds, [10, 5], False, rng_seed=77)
+    assert all(torch.equal(a, b) for u, v in zip(blocks, ref) for a, b in zip(u, v))
+    assert torch.equal(x.cpu(), feat[ref[-1][1].cpu()])
+    smp.close()
+    dist.barrier()
+    fsr.close()
     print(f"RANK {rank} OK", flush=True)
     dist.destroy_process_group()
 
