@@ -93,8 +93,7 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
     ub += e;
   }
   int64_t cap = 64;
-  static const int cap_pct = getenv("DGS_RL_CAP_PCT") ? atoi(getenv("DGS_RL_CAP_PCT")) : 200;
-  while (cap * 100 < (int64_t)cap_pct * items_max) cap <<= 1;
+  while (cap < 2 * items_max) cap <<= 1;
   const int idb = itype == DGS_I64 ? 8 : 4;
   p->S_max = S_max;
   p->E_max = E_max;
@@ -310,6 +309,7 @@ constexpr int kPkSeeds = 128;  // seeds per pick tile (256 was slower on B200: 4
 constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase (8: no gain)
 constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
+constexpr int kFloydRegs = 16; // fan-outs up to this run Floyd's sampling in registers
 
 // Seeds per pick tile: up to 128, fewer when the hop is small so that every CTA of the grid gets
 // a tile (the phases are latency chains - more CTAs in flight, not longer chains per CTA).
@@ -398,9 +398,36 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       s_deg[tid] = deg;
       s_cnt[tid] = cnt;
       cur.cnt[i] = cnt;
+      if (MODE == kUniform && k <= kFloydRegs && deg > k) {
+        // Floyd's subset sampling entirely in registers (fully unrolled, no shared-memory round
+        // trips): draw t picks r in [0, deg-k+t], or deg-k+t itself when r was already picked
+        unsigned int P[kFloydRegs];
+#pragma unroll
+        for (int q = 0; q < kFloydRegs / 4; ++q) {
+          if (4 * q < k) {
+            const uint4 r4 = Philox::gen(rng_key, (uint64_t)i, (uint64_t)q);
+            P[4 * q] = r4.x; P[4 * q + 1] = r4.y; P[4 * q + 2] = r4.z; P[4 * q + 3] = r4.w;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < kFloydRegs; ++t) {
+          if (t < k) {
+            const unsigned int J = (unsigned int)(deg - k + t);
+            const unsigned int r = rand_below(P[t], J + 1);
+            bool dup = false;
+#pragma unroll
+            for (int q = 0; q < t; ++q) dup |= (P[q] == r);
+            P[t] = dup ? J : r;
+          }
+        }
+        unsigned int *dst = s_pick + (size_t)tid * k;
+#pragma unroll
+        for (int t = 0; t < kFloydRegs; ++t)
+          if (t < k) dst[t] = P[t];
+      }
     }
     if (tile == blockIdx.x) fstamp(1);
-    if (MODE == kUniform) {
+    if (MODE == kUniform && k > kFloydRegs) {
       // random words of Floyd's draws, computed by all threads (one Philox block = 4 draws)
       const int blocks_per_seed = (k + 3) >> 2;
       for (int b = tid; b < ns * blocks_per_seed; b += kBkThreads) {
@@ -414,10 +441,9 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         if (left > 3) P[3] = r4.w;
       }
     }
-    __syncthreads();
-    if (MODE == kUniform) {
-      // Floyd's subset sampling, one THREAD per seed: draw t picks r in [0, deg-k+t], or deg-k+t
-      // itself when r was already picked (O(k^2) compares against shared memory, no traffic)
+    if (MODE != kUniform || k > kFloydRegs) __syncthreads();
+    if (MODE == kUniform && k > kFloydRegs) {
+      // Floyd's subset sampling, one THREAD per seed (O(k^2) compares against shared memory)
       if (tid < ns) {
         const int deg = s_deg[tid];
         if (deg > k) {
@@ -431,7 +457,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
           }
         }
       }
-    } else if (MODE != kUniformReplace) {
+    } else if (MODE == kBias || MODE == kBiasReplace) {
       for (int s_ = warp; s_ < ns; s_ += kBkWarps) {
         const int deg = s_deg[s_];
         if (deg == 0 || (!with_replace && deg <= k)) continue;  // copy path: position j
@@ -497,7 +523,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
 // Rank phase: CTA per 64 seeds - flags first occurrences among the seeds (A) and the sampled
 // neighbours (B), counts the edges (C), block scans, per-tile totals to prefA / prefB / prefC.
 __device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k, const HopState &cur,
-                                                 const BlocksWs &ws) {
+                                                 const BlocksWs &ws, bool unique_seeds) {
   __shared__ long long s_scan[32];
   __shared__ long long s_total;
   __shared__ int s_cnt[kBkTile];
@@ -518,7 +544,9 @@ __device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k,
       s_cnt[tid] = (int)c;
     }
     __syncthreads();
-    if (tid < ns) fa = (ldcg(&cur.table[slot_a].first) == (unsigned int)(i0 + tid)) ? 1 : 0;
+    // seeds that are a previous frontier are distinct: each is its own first occurrence
+    if (tid < ns)
+      fa = (unique_seeds || ldcg(&cur.table[slot_a].first) == (unsigned int)(i0 + tid)) ? 1 : 0;
     long long carry = 0;
     long long totA = 0, totC = 0;
     for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
@@ -621,16 +649,20 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
                                            int k, const IdT *__restrict__ pad_col,
                                            const HopState &cur, const BlocksWs &ws,
                                            IdT *__restrict__ frontier, IdT *__restrict__ out_row,
-                                           IdT *__restrict__ out_col) {
+                                           IdT *__restrict__ out_col, bool unique_seeds) {
   const int64_t tiles = (S + kBkTile - 1) / kBkTile;
   const long long totA = ldcg(ws.prefA + tiles);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) *ws.pending_S = S;  // this hop's table is dirty until the next pick phase wipes it
-  for (int64_t i = tid; i < S; i += stride) {
-    const RlSlot s = ldcg_slot(&cur.table[ldcg(cur.pos_seed + i)]);
-    if (s.first == (unsigned int)i)
-      frontier[ldcg(ws.prefA + i / kBkTile) + (long long)s.lrank] = ldcg(seeds + i);
+  if (unique_seeds) {   // new id of seed i is i
+    for (int64_t i = tid; i < S; i += stride) frontier[i] = ldcg(seeds + i);
+  } else {
+    for (int64_t i = tid; i < S; i += stride) {
+      const RlSlot s = ldcg_slot(&cur.table[ldcg(cur.pos_seed + i)]);
+      if (s.first == (unsigned int)i)
+        frontier[ldcg(ws.prefA + i / kBkTile) + (long long)s.lrank] = ldcg(seeds + i);
+    }
   }
   if (k <= 0) return;
   const int64_t E = S * k;
@@ -648,7 +680,7 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
         jj[u] = (int)(e - si[u] * k);
         ok[u] = jj[u] < ldcg(cur.cnt + si[u]);
         pc[u] = ldcg(cur.pos_col + e);
-        ps[u] = ldcg(cur.pos_seed + si[u]);
+        if (!unique_seeds) ps[u] = ldcg(cur.pos_seed + si[u]);
       }
     }
     unsigned int cf[kEmBatch], cr[kEmBatch], sf[kEmBatch], sr[kEmBatch];
@@ -656,9 +688,11 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
     for (int u = 0; u < kEmBatch; ++u) {
       if (ok[u]) {
         const int2 c2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[pc[u]].first));
-        const int2 s2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[ps[u]].first));
         cf[u] = (unsigned int)c2.x; cr[u] = (unsigned int)c2.y;
-        sf[u] = (unsigned int)s2.x; sr[u] = (unsigned int)s2.y;
+        if (!unique_seeds) {
+          const int2 s2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[ps[u]].first));
+          sf[u] = (unsigned int)s2.x; sr[u] = (unsigned int)s2.y;
+        }
       }
     }
 #pragma unroll
@@ -670,7 +704,8 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
         sc.lrank = cr[u];
         const long long cid = new_id(sc, S_ub, k, totA, ws.prefA, ws.prefB);
         if ((int64_t)cf[u] == S_ub + e) frontier[cid] = ldcg(pad_col + e);
-        const long long rid = ldcg(ws.prefA + sf[u] / kBkTile) + (long long)sr[u];
+        const long long rid =
+            unique_seeds ? (long long)si[u] : ldcg(ws.prefA + sf[u] / kBkTile) + (long long)sr[u];
         const long long o = ldcg(ws.prefC + si[u] / kBkTile) + (long long)ldcg(ws.loff + si[u]) + jj[u];
         out_row[o] = (IdT)rid;
         out_col[o] = (IdT)cid;
@@ -696,10 +731,11 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
 
 __global__ void __launch_bounds__(kBkThreads)
 fused_rank_kernel(int64_t S_ub, const int64_t *__restrict__ S_dev, int k, HopState cur,
-                  BlocksWs ws, int64_t *__restrict__ out_nnz, int64_t *__restrict__ out_nfront) {
+                  BlocksWs ws, int64_t *__restrict__ out_nnz, int64_t *__restrict__ out_nfront,
+                  int unique_seeds) {
   __shared__ bool s_last;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
-  rank_tiles_phase(S_ub, S, k, cur, ws);
+  rank_tiles_phase(S_ub, S, k, cur, ws, unique_seeds != 0);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -718,9 +754,10 @@ template <typename IdT>
 __global__ void __launch_bounds__(kBkThreads)
 fused_emit_kernel(const IdT *__restrict__ seeds, int64_t S_ub, const int64_t *__restrict__ S_dev,
                   int k, const IdT *__restrict__ pad_col, HopState cur, BlocksWs ws,
-                  IdT *__restrict__ frontier, IdT *__restrict__ out_row, IdT *__restrict__ out_col) {
+                  IdT *__restrict__ frontier, IdT *__restrict__ out_row, IdT *__restrict__ out_col,
+                  int unique_seeds) {
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
-  emit_phase<IdT>(seeds, S_ub, S, k, pad_col, cur, ws, frontier, out_row, out_col);
+  emit_phase<IdT>(seeds, S_ub, S, k, pad_col, cur, ws, frontier, out_row, out_col, unique_seeds != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -740,7 +777,6 @@ struct BatchArgs {
   int L;
   uint64_t cap_mask;
   unsigned long long *trace;  // debug: %globaltimer stamps of CTA 0 around every phase
-  int wipe_first;
   HopArgs hop[8];
 };
 
@@ -763,19 +799,15 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     const HopState &prev = ws.hop[h.cur ^ 1];
     const long long pS_live = ldcg(ws.pending_S);
     const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
-    if (a.wipe_first)
-      wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
-               (int64_t)a.cap_mask + 1);
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
                                    (IdT *)ws.pad_col, cur, a.cap_mask,
                                    a.trace ? a.trace + 256 + 8 * l : nullptr);
-    if (!a.wipe_first)
-      wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
+    wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
                (int64_t)a.cap_mask + 1);
     stamp();
     grid.sync();
     stamp();
-    rank_tiles_phase(h.S_ub, S, h.k, cur, ws);
+    rank_tiles_phase(h.S_ub, S, h.k, cur, ws, l > 0);
     stamp();
     {
       __shared__ bool s_last;
@@ -793,7 +825,7 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     grid.sync();
     stamp();
     emit_phase<IdT>((const IdT *)h.seeds, h.S_ub, S, h.k, (const IdT *)ws.pad_col, cur, ws,
-                    (IdT *)h.frontier, (IdT *)h.out_row, (IdT *)h.out_col);
+                    (IdT *)h.frontier, (IdT *)h.out_row, (IdT *)h.out_col, l > 0);
     stamp();
     grid.sync();
     stamp();
@@ -858,8 +890,6 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     memset(&a, 0, sizeof(a));
     a.L = L;
     a.cap_mask = cap_mask;
-    static const int wipe_first = getenv("DGS_WIPE_FIRST") ? atoi(getenv("DGS_WIPE_FIRST")) : 0;
-    a.wipe_first = wipe_first;
     for (int l = 0; l < L; ++l) {
       HopArgs &h = a.hop[l];
       const int pl = l > 0 ? l - 1 : L - 1;
@@ -1008,13 +1038,14 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
     DGS_LAUNCH_CHECK();
     mark();
     const int grid_rank = grid_for(cur_ub, kBkTile, 8);
-    fused_rank_kernel<<<grid_rank, kBkThreads, 0, st>>>(cur_ub, cur_dev, k, cur, ws, nnz_dev, nf_dev);
+    fused_rank_kernel<<<grid_rank, kBkThreads, 0, st>>>(cur_ub, cur_dev, k, cur, ws, nnz_dev, nf_dev,
+                                                        l > 0 ? 1 : 0);
     DGS_LAUNCH_CHECK();
     mark();
     const int grid_emit = grid_for(cur_ub + nnz_ub, kBkThreads * 2, 8);
     fused_emit_kernel<IdT><<<grid_emit, kBkThreads, 0, st>>>(
         cur_seeds, cur_ub, cur_dev, k, (const IdT *)ws.pad_col, cur, ws, (IdT *)out_frontier[l],
-        (IdT *)out_row[l], (IdT *)out_col[l]);
+        (IdT *)out_row[l], (IdT *)out_col[l], l > 0 ? 1 : 0);
     DGS_LAUNCH_CHECK();
     mark();
     cur_seeds = (const IdT *)out_frontier[l];
