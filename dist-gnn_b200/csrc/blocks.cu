@@ -55,11 +55,37 @@ struct __align__(16) RlSlot {
   unsigned int lrank;  // rank of that first occurrence inside its tile
 };
 
+// One relabel table.  Hashed (direct == 0): open addressing over 16-byte RlSlot, any id.  Direct
+// (direct == 1): the caller told us the number of nodes, so the slot of an id IS the id - 8 bytes
+// {first, lrank} per node, no key, no probing, and an insert is ONE fire-and-forget atomicMin
+// instead of a CAS whose result the thread has to wait for plus an atomicMin (measured on B200,
+// products shape: 93 vs 107 us per batch).  180 GB of HBM pay for 16 bytes per node.
+struct Tab {
+  char *base;
+  int direct;
+  __device__ __forceinline__ unsigned int *first(uint64_t pos) const {
+    return reinterpret_cast<unsigned int *>(base + (direct ? pos * 8 : pos * 16 + 8));
+  }
+  __device__ __forceinline__ unsigned int *lrank(uint64_t pos) const { return first(pos) + 1; }
+  __device__ __forceinline__ unsigned long long *key(uint64_t pos) const {
+    return reinterpret_cast<unsigned long long *>(base + pos * 16);
+  }
+  __device__ __forceinline__ int2 first_lrank(uint64_t pos) const {   // L2 load of {first, lrank}
+    return __ldcg(reinterpret_cast<const int2 *>(first(pos)));
+  }
+  __device__ __forceinline__ void wipe(uint64_t pos) const {
+    if (direct)
+      *reinterpret_cast<long long *>(base + pos * 8) = -1;
+    else
+      *reinterpret_cast<int4 *>(base + pos * 16) = make_int4(-1, -1, -1, -1);
+  }
+};
+
 struct HopState {        // per-hop arrays that must survive until the next hop's cleanup
   int *cnt;              // [S_max]   edges kept for seed i
   unsigned int *pos_seed;  // [S_max]   table slot of seed i
   unsigned int *pos_col;   // [E_max]   table slot of padded neighbour slot e
-  RlSlot *table;
+  Tab table;
 };
 
 struct BlocksWs {
@@ -70,16 +96,18 @@ struct BlocksWs {
   void *pad_col;                     // [E_max] ids
   HopState hop[2];
   int64_t cap;                       // slots per table
+  int direct;                        // tables are direct-addressed (see Tab)
 };
 
 struct BlocksPlan {
-  int64_t S_max, E_max, tiles_max, cap, bytes;
+  int64_t S_max, E_max, tiles_max, cap, bytes, table_bytes;
+  int direct;
 };
 
 static inline int64_t up256(int64_t x) { return (x + 255) / 256 * 256; }
 
-static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_out, BlocksPlan *p,
-                       char *base, BlocksWs *ws) {
+static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_out, int64_t num_nodes,
+                       BlocksPlan *p, char *base, BlocksWs *ws) {
   DGS_REQUIRE(L >= 1 && L <= 16, "sample_blocks: 1..16 layers supported");
   int64_t ub = num_seeds < 1 ? 1 : num_seeds, S_max = 1, E_max = 1, items_max = 1;
   for (int l = 0; l < L; ++l) {
@@ -94,6 +122,13 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
   }
   int64_t cap = 64;
   while (cap < 2 * items_max) cap <<= 1;
+  // direct addressing when the node count is known, ids fit the 32-bit slot arrays and two tables
+  // of 8 bytes per node stay within 8 GiB
+  static const bool no_direct = getenv("DGS_BLOCKS_HASHED") != nullptr;
+  const bool direct = !no_direct && num_nodes > 0 && num_nodes < (1ll << 32) - 2 && num_nodes <= (1ll << 29);
+  if (direct) cap = (num_nodes + 1) & ~1ll;   // even: the linear wipe stores 16 bytes at a time
+  p->direct = direct ? 1 : 0;
+  p->table_bytes = cap * (direct ? 8 : (int64_t)sizeof(RlSlot));
   const int idb = itype == DGS_I64 ? 8 : 4;
   p->S_max = S_max;
   p->E_max = E_max;
@@ -115,7 +150,7 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
     h[b][0] = take(S_max * 4);
     h[b][1] = take(S_max * 4);
     h[b][2] = take(E_max * 4);
-    h[b][3] = take(cap * (int64_t)sizeof(RlSlot));
+    h[b][3] = take(p->table_bytes);
   }
   p->bytes = off;
   if (ws) {
@@ -130,23 +165,29 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
       ws->hop[b].cnt = (int *)h[b][0];
       ws->hop[b].pos_seed = (unsigned int *)h[b][1];
       ws->hop[b].pos_col = (unsigned int *)h[b][2];
-      ws->hop[b].table = (RlSlot *)h[b][3];
+      ws->hop[b].table.base = h[b][3];
+      ws->hop[b].table.direct = p->direct;
     }
     ws->cap = cap;
+    ws->direct = p->direct;
   }
   return 0;
 }
 
-__device__ __forceinline__ unsigned int rl_insert(RlSlot *table, uint64_t mask, long long key,
+__device__ __forceinline__ unsigned int rl_insert(const Tab &table, uint64_t mask, long long key,
                                                   unsigned int item) {
+  if (table.direct) {
+    atomicMin(table.first((uint64_t)key), item);
+    return (unsigned int)key;
+  }
   uint64_t pos = mix64((uint64_t)key) & mask;
   while (true) {
-    unsigned long long prev = atomicCAS((unsigned long long *)&table[pos].key,
-                                        (unsigned long long)kEmptyKey, (unsigned long long)key);
+    unsigned long long prev =
+        atomicCAS(table.key(pos), (unsigned long long)kEmptyKey, (unsigned long long)key);
     if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)key) break;
     pos = (pos + 1) & mask;
   }
-  atomicMin(&table[pos].first, item);
+  atomicMin(table.first(pos), item);
   return (unsigned int)pos;
 }
 
@@ -156,34 +197,40 @@ __device__ __forceinline__ unsigned int rl_insert(RlSlot *table, uint64_t mask, 
 // of a hop's sampled ids are duplicates) - fewer atomics but two dependent round trips for every
 // first insert; slower overall on B200 (118 vs 103 us per batch), so not used.
 template <int N>
-__device__ __forceinline__ void rl_insert_batch(RlSlot *table, uint64_t mask, const long long (&key)[N],
+__device__ __forceinline__ void rl_insert_batch(const Tab &table, uint64_t mask, const long long (&key)[N],
                                                 const unsigned int (&item)[N], const bool (&ok)[N],
                                                 unsigned int (&out_pos)[N]) {
+  if (table.direct) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      if (ok[u]) {
+        atomicMin(table.first((uint64_t)key[u]), item[u]);
+        out_pos[u] = (unsigned int)key[u];
+      }
+    }
+    return;
+  }
   uint64_t pos[N];
   unsigned long long prev[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
     pos[u] = mix64((uint64_t)key[u]) & mask;
     if (ok[u])
-      prev[u] = atomicCAS((unsigned long long *)&table[pos[u]].key, (unsigned long long)kEmptyKey,
-                          (unsigned long long)key[u]);
+      prev[u] = atomicCAS(table.key(pos[u]), (unsigned long long)kEmptyKey, (unsigned long long)key[u]);
   }
 #pragma unroll
   for (int u = 0; u < N; ++u) {
     if (!ok[u]) continue;
     while (prev[u] != (unsigned long long)kEmptyKey && prev[u] != (unsigned long long)key[u]) {
       pos[u] = (pos[u] + 1) & mask;
-      prev[u] = atomicCAS((unsigned long long *)&table[pos[u]].key, (unsigned long long)kEmptyKey,
-                          (unsigned long long)key[u]);
+      prev[u] = atomicCAS(table.key(pos[u]), (unsigned long long)kEmptyKey, (unsigned long long)key[u]);
     }
-    atomicMin(&table[pos[u]].first, item[u]);
+    atomicMin(table.first(pos[u]), item[u]);
     out_pos[u] = (unsigned int)pos[u];
   }
 }
 
-__device__ __forceinline__ void rl_wipe(RlSlot *table, unsigned int pos) {
-  *reinterpret_cast<int4 *>(&table[pos]) = make_int4(-1, -1, -1, -1);
-}
+__device__ __forceinline__ void rl_wipe(const Tab &table, unsigned int pos) { table.wipe(pos); }
 
 // Wipe every slot the given hop touched (idempotent; duplicates wipe the same slot twice).
 // busy_ctas: CTAs [0, busy_ctas) have sampling work of their own in this phase; when enough idle
@@ -203,10 +250,13 @@ __device__ __forceinline__ void wipe_hop(const HopState &h, int64_t S, int k, in
   }
   const int64_t stride = vgrid * blockDim.x;
   const int64_t tid = vbid * blockDim.x + threadIdx.x;
-  if (items * 8 > cap) {
-    int4 *t = reinterpret_cast<int4 *>(h.table);
+  // linear wipe = cap (hashed) or cap / 2 (direct) coalesced 16-byte stores; scattered = one
+  // store per item at roughly 8x the cost of a coalesced one
+  const int64_t n16 = h.table.direct ? cap / 2 : cap;
+  if (items * 8 > n16) {
+    int4 *t = reinterpret_cast<int4 *>(h.table.base);
     const int4 e = make_int4(-1, -1, -1, -1);
-    for (int64_t i = tid; i < cap; i += stride) t[i] = e;
+    for (int64_t i = tid; i < n16; i += stride) t[i] = e;
     return;
   }
   for (int64_t i = tid; i < S; i += stride) rl_wipe(h.table, __ldcg(h.pos_seed + i));
@@ -236,7 +286,7 @@ template <typename IdT>
 struct PadEmit {
   IdT *pcol;
   unsigned int *ppos;
-  RlSlot *table;
+  Tab table;
   uint64_t mask;
   unsigned int item_base;
   __device__ __forceinline__ void operator()(int j, IdT v) {
@@ -252,7 +302,7 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
                   HopState cur, uint64_t cap_mask, HopState prev, int64_t prev_S_ub,
                   const long long *__restrict__ prev_S_dev, int prev_k, int gmem_scratch) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
-  const long long pS_live = prev.table != nullptr ? *prev_S_dev : 0;
+  const long long pS_live = prev.table.base != nullptr ? *prev_S_dev : 0;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
@@ -296,7 +346,7 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
                                         w_idx, w_key, emit);
   }
   // wipe the other table: the slots the previous hop touched
-  if (prev.table != nullptr) wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, gridDim.x, (int64_t)cap_mask + 1);
+  if (prev.table.base != nullptr) wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, gridDim.x, (int64_t)cap_mask + 1);
 }
 
 
@@ -323,15 +373,6 @@ template <typename T>
 __device__ __forceinline__ T ldcg(const T *p) {
   return __ldcg(p);
 }
-__device__ __forceinline__ RlSlot ldcg_slot(const RlSlot *p) {
-  const int4 raw = __ldcg(reinterpret_cast<const int4 *>(p));
-  RlSlot s;
-  s.key = ((long long)(uint32_t)raw.y << 32) | (uint32_t)raw.x;
-  s.first = (unsigned int)raw.z;
-  s.lrank = (unsigned int)raw.w;
-  return s;
-}
-
 template <typename IdT>
 struct PosEmit {
   unsigned int *p;
@@ -384,9 +425,14 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       // first probe of the seed's own table insert: issued now, resolved after the neighbours'
       // (its round trip overlaps the indptr loads, the selection and the row loads)
       seed_nid = nid;
-      seed_pos = mix64((uint64_t)nid) & cap_mask;
-      seed_prev = atomicCAS((unsigned long long *)&cur.table[seed_pos].key,
-                            (unsigned long long)kEmptyKey, (unsigned long long)nid);
+      if (cur.table.direct) {
+        seed_pos = (uint64_t)nid;
+        seed_prev = (unsigned long long)nid;
+      } else {
+        seed_pos = mix64((uint64_t)nid) & cap_mask;
+        seed_prev = atomicCAS(cur.table.key(seed_pos), (unsigned long long)kEmptyKey,
+                              (unsigned long long)nid);
+      }
       int dev;
       long long begin, deg64;
       resolve_seed<ET>(g, nid, &dev, &begin, &deg64);
@@ -509,10 +555,10 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
     if (tid < ns) {
       while (seed_prev != (unsigned long long)kEmptyKey && seed_prev != (unsigned long long)seed_nid) {
         seed_pos = (seed_pos + 1) & cap_mask;
-        seed_prev = atomicCAS((unsigned long long *)&cur.table[seed_pos].key,
-                              (unsigned long long)kEmptyKey, (unsigned long long)seed_nid);
+        seed_prev = atomicCAS(cur.table.key(seed_pos), (unsigned long long)kEmptyKey,
+                              (unsigned long long)seed_nid);
       }
-      atomicMin(&cur.table[seed_pos].first, (unsigned int)(i0 + tid));
+      atomicMin(cur.table.first(seed_pos), (unsigned int)(i0 + tid));
       cur.pos_seed[i0 + tid] = (unsigned int)seed_pos;
     }
     if (tile == blockIdx.x) fstamp(3);
@@ -546,7 +592,7 @@ __device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k,
     __syncthreads();
     // seeds that are a previous frontier are distinct: each is its own first occurrence
     if (tid < ns)
-      fa = (unique_seeds || ldcg(&cur.table[slot_a].first) == (unsigned int)(i0 + tid)) ? 1 : 0;
+      fa = (unique_seeds || ldcg(cur.table.first(slot_a)) == (unsigned int)(i0 + tid)) ? 1 : 0;
     long long carry = 0;
     long long totA = 0, totC = 0;
     for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
@@ -566,13 +612,13 @@ __device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k,
       unsigned int first[kRkItems];
 #pragma unroll
       for (int u = 0; u < kRkItems; ++u)
-        if (valid[u]) first[u] = ldcg(&cur.table[slot[u]].first);
+        if (valid[u]) first[u] = ldcg(cur.table.first(slot[u]));
       if (base == 0) {
         // A and C share one packed scan (A in the high half)
         const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
         totA = s_total >> 32;
         totC = s_total & 0xffffffffll;
-        if (fa) cur.table[slot_a].lrank = (unsigned int)(rac >> 32);
+        if (fa) *cur.table.lrank(slot_a) = (unsigned int)(rac >> 32);
         if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
       }
       int mine = 0;
@@ -585,7 +631,7 @@ __device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k,
       long long r = carry + block_exclusive_scan<long long>((long long)mine, s_scan, &s_total);
 #pragma unroll
       for (int u = 0; u < kRkItems; ++u)
-        if (fb[u]) cur.table[slot[u]].lrank = (unsigned int)(r++);
+        if (fb[u]) *cur.table.lrank(slot[u]) = (unsigned int)(r++);
       carry += s_total;
     }
     if (tid == 0) {
@@ -659,9 +705,9 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
     for (int64_t i = tid; i < S; i += stride) frontier[i] = ldcg(seeds + i);
   } else {
     for (int64_t i = tid; i < S; i += stride) {
-      const RlSlot s = ldcg_slot(&cur.table[ldcg(cur.pos_seed + i)]);
-      if (s.first == (unsigned int)i)
-        frontier[ldcg(ws.prefA + i / kBkTile) + (long long)s.lrank] = ldcg(seeds + i);
+      const int2 fl = cur.table.first_lrank(ldcg(cur.pos_seed + i));
+      if ((unsigned int)fl.x == (unsigned int)i)
+        frontier[ldcg(ws.prefA + i / kBkTile) + (long long)(unsigned int)fl.y] = ldcg(seeds + i);
     }
   }
   if (k <= 0) return;
@@ -687,10 +733,10 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
 #pragma unroll
     for (int u = 0; u < kEmBatch; ++u) {
       if (ok[u]) {
-        const int2 c2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[pc[u]].first));
+        const int2 c2 = cur.table.first_lrank(pc[u]);
         cf[u] = (unsigned int)c2.x; cr[u] = (unsigned int)c2.y;
         if (!unique_seeds) {
-          const int2 s2 = __ldcg(reinterpret_cast<const int2 *>(&cur.table[ps[u]].first));
+          const int2 s2 = cur.table.first_lrank(ps[u]);
           sf[u] = (unsigned int)s2.x; sr[u] = (unsigned int)s2.y;
         }
       }
@@ -1070,24 +1116,27 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
 using namespace dgsb;
 
 extern "C" int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
-                                              const int64_t *fan_out) {
+                                              const int64_t *fan_out, int64_t num_nodes) {
   BlocksPlan p;
-  if (!fan_out || blocks_plan(itype, num_seeds, num_layers, fan_out, &p, nullptr, nullptr)) return -1;
+  if (!fan_out || blocks_plan(itype, num_seeds, num_layers, fan_out, num_nodes, &p, nullptr, nullptr))
+    return -1;
   return p.bytes;
 }
 
 extern "C" int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
-                                         int num_layers, const int64_t *fan_out, void *stream) {
+                                         int num_layers, const int64_t *fan_out, int64_t num_nodes,
+                                         void *stream) {
   DGS_REQUIRE(ws && fan_out, "dgs_sample_blocks_ws_init: null argument");
   BlocksPlan p;
   BlocksWs w;
-  if (blocks_plan(itype, num_seeds, num_layers, fan_out, &p, (char *)ws, &w)) return 1;
+  if (blocks_plan(itype, num_seeds, num_layers, fan_out, num_nodes, &p, (char *)ws, &w)) return 1;
   DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks_ws_init: workspace %lld < %lld bytes",
               (long long)ws_bytes, (long long)p.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   DGS_CUDA_OK(cudaMemsetAsync(w.done, 0, 256, st));
   for (int b = 0; b < 2; ++b) {
-    blocks_ws_init_kernel<<<grid_for(p.cap, 256, 8), 256, 0, st>>>((int4 *)w.hop[b].table, p.cap);
+    blocks_ws_init_kernel<<<grid_for(p.table_bytes / 16, 256, 8), 256, 0, st>>>(
+        (int4 *)w.hop[b].table.base, p.table_bytes / 16);
     DGS_LAUNCH_CHECK();
   }
   return 0;
@@ -1117,7 +1166,7 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
   DGS_REQUIRE(seeds != nullptr, "dgs_sample_blocks: null seeds");
   BlocksPlan p;
   BlocksWs w;
-  if (blocks_plan(g->itype, num_seeds, num_layers, fan_out, &p, (char *)ws, &w)) return 1;
+  if (blocks_plan(g->itype, num_seeds, num_layers, fan_out, g->num_nodes, &p, (char *)ws, &w)) return 1;
   DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks: workspace %lld < %lld bytes",
               (long long)ws_bytes, (long long)p.bytes);
   GraphSrc src;

@@ -30,6 +30,7 @@ class Graph(C.Structure):
         ("loc_table", c_vp),
         ("loc_capacity", c_i64),
         ("loc_mod_world", C.c_int32),
+        ("num_nodes", c_i64),
     ]
 
 
@@ -77,8 +78,8 @@ SIGNATURES = {
     "dgs_sample_ws_bytes": (c_i64, [c_i64]),
     "dgs_sample_neighbors": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, c_vp, c_i64, C.c_int,
                                        C.c_uint64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "dgs_sample_blocks_ws_bytes": (c_i64, [C.c_int, c_i64, C.c_int, c_i64p]),
-    "dgs_sample_blocks_ws_init": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, C.c_int, c_i64p, c_vp]),
+    "dgs_sample_blocks_ws_bytes": (c_i64, [C.c_int, c_i64, C.c_int, c_i64p, c_i64]),
+    "dgs_sample_blocks_ws_init": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, C.c_int, c_i64p, c_i64, c_vp]),
     "dgs_sample_blocks": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, C.c_int, c_i64p, C.c_int,
                                     C.c_uint64, c_vpp, c_vpp, c_vpp, c_i64p, c_i64p, c_vp, c_vp,
                                     c_i64, c_i64, c_vp, c_vp]),
@@ -109,7 +110,7 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if l.dgs_abi_version() != 1:
+        if l.dgs_abi_version() != 2:
             raise RuntimeError("dgs_b200: ABI version mismatch")
         _lib = l
     return _lib

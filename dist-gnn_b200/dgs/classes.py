@@ -250,11 +250,12 @@ class _BlockPipeline:
             if total <= MAX_FUSED_ELEMS:
                 fo = _lib.i64_array(fan_out)
                 it = ID_DTYPES[self._id_dtype]
-                nbytes = l.dgs_sample_blocks_ws_bytes(it, S, L, fo)
+                nbytes = l.dgs_sample_blocks_ws_bytes(it, S, L, fo, self._graph.num_nodes)
                 if nbytes < 0:
                     raise RuntimeError("sample_blocks: " + l.dgs_last_error().decode())
                 ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
-                check(l.dgs_sample_blocks_ws_init(ptr(ws), nbytes, it, S, L, fo, stream()),
+                check(l.dgs_sample_blocks_ws_init(ptr(ws), nbytes, it, S, L, fo,
+                                                  self._graph.num_nodes, stream()),
                       "sample_blocks_ws_init")
                 es = torch.empty(0, dtype=self._id_dtype).element_size()
                 offs, off = [], 0
@@ -380,6 +381,7 @@ class CSRSampler:
         if device is None:
             device = indices.device if indices.is_cuda else torch.device("cuda", torch.cuda.current_device())
         g = ops._make_graph(indptr, indices, probs if probs is not None and probs.numel() else None)
+        g.num_nodes = indptr.numel() - 1    # known node count: direct-addressed relabel tables
         self._pipe = _BlockPipeline(g, device, indices.dtype)
 
     def _CAPI_sample_node_classifiction(self, seeds, fan_out, replace=False, rng_seed=None):
@@ -450,6 +452,7 @@ class P2PCacheSampler:
             loc_pr = self.gpu_probs_._CAPI_get_local_device_tensor() if self.bias_ else None
             self._graph = ops._make_graph(self.gpu_indptr_._CAPI_get_local_device_tensor(),
                                           self.gpu_indices_._CAPI_get_local_device_tensor(), loc_pr)
+            self._graph.num_nodes = num_nodes
             self._pipe = _BlockPipeline(self._graph, self._device, sub_indices.dtype)
             return
         g = _lib.Graph()
@@ -464,6 +467,7 @@ class P2PCacheSampler:
         g.loc_table = ptr(self._table) if self._table is not None else None
         g.loc_capacity = self._cap
         g.loc_mod_world = self._mod_world
+        g.num_nodes = num_nodes
         self._graph = g
         self._pipe = _BlockPipeline(g, self._device, sub_indices.dtype)
 

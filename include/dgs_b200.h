@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DGS_B200_ABI_VERSION 1
+#define DGS_B200_ABI_VERSION 2
 #define DGS_MAX_DEVICES 16
 
 typedef enum { DGS_I32 = 0, DGS_I64 = 1 } dgs_itype_t;
@@ -170,6 +170,10 @@ typedef struct {
    * slot n / world - the owner is computed, loc_table is not read (extension; the layout of the
    * sharded benchmarks). */
   int32_t loc_mod_world;
+  /* number of nodes of the graph (ids are < num_nodes), 0 = unknown.  Only dgs_sample_blocks uses
+   * it: with it the relabel tables are direct-addressed (8 bytes per node, one atomic per insert)
+   * instead of hashed. */
+  int64_t num_nodes;
 } dgs_graph_t;
 
 /* Workspace size (bytes) for a call over at most max_seeds seeds.  The first 256 bytes must be
@@ -198,7 +202,7 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
  * Capacities: cap_edges[l] >= ub_l * k_l, cap_frontier[l] >= ub_l * (1 + k_l) with
  * ub_0 = num_seeds, ub_{l+1} = ub_l * (1 + k_l).
  * ws: dgs_sample_blocks_ws_bytes(...) bytes, initialised ONCE with dgs_sample_blocks_ws_init for
- * the same (itype, num_seeds, num_layers, fan_out); epoch = number of dgs_sample_blocks calls
+ * the same (itype, num_seeds, num_layers, fan_out, num_nodes = g->num_nodes); epoch = number of dgs_sample_blocks calls
  * already made on this workspace since its init (0, 1, 2, ...): the relabel table a call leaves
  * dirty is wiped by the first kernel of the next call, which needs to know which of the two
  * alternating tables that is.  One cooperative launch per batch (or 3 kernels per hop when the
@@ -206,9 +210,9 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
  * counts_host (optional, pinned host memory, 2 L int64): when non-NULL the counts are copied back
  * and the stream is synchronised before returning - the single host round trip of a batch. */
 int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
-                                   const int64_t *fan_out);
+                                   const int64_t *fan_out, int64_t num_nodes);
 int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
-                              int num_layers, const int64_t *fan_out, void *stream);
+                              int num_layers, const int64_t *fan_out, int64_t num_nodes, void *stream);
 int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds, int num_layers,
                       const int64_t *fan_out, int replace, uint64_t rng_seed,
                       void *const *out_frontier, void *const *out_row, void *const *out_col,

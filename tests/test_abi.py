@@ -30,7 +30,7 @@ def test_header_symbols_exported():
 def test_version_and_error_channel():
     from dgs import _lib
     lib = _lib.lib()
-    assert lib.dgs_abi_version() == 1
+    assert lib.dgs_abi_version() == 2
     assert lib.dgs_launch_count() == 0 or lib.dgs_launch_count() > 0
     # argument error: reported through the return code + dgs_last_error, nothing launched
     before = lib.dgs_launch_count()

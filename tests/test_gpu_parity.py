@@ -597,6 +597,28 @@ print(h.hexdigest())
     assert digests[0] == digests[1]
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("bias", [False, True])
+def test_fused_blocks_direct_equals_hashed_tables(dgs, cuda, idt, bias):
+    """The relabel tables of the fused path are direct-addressed when the node count is known
+    (dgs_graph_t.num_nodes) and hashed otherwise: both must give the same blocks, batch after batch
+    (the tables are wiped and reused), including duplicate seeds and a node count that is odd."""
+    N = 30001
+    indptr, indices, probs = dgs_synth.make_csr(N, 600000, seed=51, weights=bias, classes=6, id_dtype=idt)
+    args = (indptr.to(idt).to(cuda), indices.to(cuda), probs.to(cuda) if bias else None)
+    direct, hashed = dgs.classes.CSRSampler(*args), dgs.classes.CSRSampler(*args)
+    assert direct._pipe._graph.num_nodes == N
+    hashed._pipe._graph.num_nodes = 0
+    g = torch.Generator().manual_seed(9)
+    for it in range(6):
+        seeds = torch.randint(0, N, (777,), generator=g).to(idt).to(cuda)
+        seeds[-1] = N - 1
+        for fan, rep in (([15, 10, 5], False), ([4, 3], True)):
+            a = direct._CAPI_sample_node_classifiction(seeds, fan, rep, rng_seed=it)
+            b = hashed._CAPI_sample_node_classifiction(seeds, fan, rep, rng_seed=it)
+            assert all(torch.equal(x, y) for u, v in zip(a, b) for x, y in zip(u, v))
+
+
 @pytest.mark.parametrize("bias", [False, True])
 def test_huge_num_picks_uses_output_scratch(dgs, cuda, bias):
     """num_picks far beyond what shared memory holds (the reference asserts num_picks <= 32 for the
