@@ -480,8 +480,9 @@ def run_b200(args, fan_out):
                    "peak_source": peak_src, "traffic": traffic.get("sample"),
                    "algorithmic_bytes": "sum over hops of 24 (S + nnz) [sample] + 8 (S + nnz) + 32 nnz + 8 U [relabel]",
                    "avg_launch_ms": sm_ms / K,
-                   "note": "latency-bound at batch %d: dependent load / atomic chains and 9 grid "
-                           "barriers, not bandwidth (DESIGN.md section 5)" % args.batch}
+                   "note": "not bandwidth-bound at batch %d: limited by the issue rate of uncoalesced "
+                           "accesses / random atomics and by 9 dependent phases with grid barriers "
+                           "(DESIGN.md section 5, profiles/r01_rt_probe.txt)" % args.batch}
     dominant, other = (roof_sample, roof_extract) if sm_ms >= ex_ms else (roof_extract, roof_sample)
     dominant = dict(dominant)
     dominant["share_of_gpu_time"] = max(sm_ms, ex_ms) / (sm_ms + ex_ms)
