@@ -360,6 +360,7 @@ constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick p
 constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
 constexpr int kFloydRegs = 16; // fan-outs up to this run Floyd's sampling in registers
+constexpr int kHubDeg = 512;   // biased sampling: rows longer than this are scanned by the whole CTA (measured: 2048 slower)
 
 // Seeds per pick tile: up to 128, fewer when the hop is small so that every CTA of the grid gets
 // a tile (the phases are latency chains - more CTAs in flight, not longer chains per CTA).
@@ -406,6 +407,9 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
   __shared__ const float *s_w[kPkSeeds];
   __shared__ int s_deg[kPkSeeds];
   __shared__ int s_cnt[kPkSeeds];
+  __shared__ int s_next;                       // next seed of the tile to hand to a warp
+  __shared__ float s_mkey[kBkWarps][32];       // hub rows: per-warp reservoirs to merge
+  __shared__ int s_midx[kBkWarps][32];
   unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
   float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -504,14 +508,52 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         }
       }
     } else if (MODE == kBias || MODE == kBiasReplace) {
-      for (int s_ = warp; s_ < ns; s_ += kBkWarps) {
+      // The weight scan of a row costs its degree, and the degrees of sampled neighbours are
+      // size-biased (hubs everywhere from the second hop on).  Rows up to kHubDeg go one per
+      // warp, handed out dynamically; a longer row is shared by all warps of the CTA.
+      const bool hubs_shared = MODE == kBias && k <= 32;
+      if (tid == 0) s_next = kBkWarps;
+      __syncthreads();
+      for (int s_ = warp; s_ < ns;) {
         const int deg = s_deg[s_];
-        if (deg == 0 || (!with_replace && deg <= k)) continue;  // copy path: position j
-        PosEmit<IdT> pe{s_pick + (size_t)s_ * k};
-        warp_select<IdT, MODE, PosEmit<IdT>, true>(nullptr, s_w[s_], deg, k, false, rng_key,
-                                                   (uint64_t)(i0 + s_), lane,
-                                                   reinterpret_cast<int *>(pe.p),
-                                                   s_key + (size_t)warp * k, pe);
+        const bool skip = deg == 0 || (!with_replace && deg <= k) || (hubs_shared && deg > kHubDeg);
+        if (!skip) {   // (copy path: position j, nothing to select)
+          PosEmit<IdT> pe{s_pick + (size_t)s_ * k};
+          warp_select<IdT, MODE, PosEmit<IdT>, true>(nullptr, s_w[s_], deg, k, false, rng_key,
+                                                     (uint64_t)(i0 + s_), lane,
+                                                     reinterpret_cast<int *>(pe.p),
+                                                     s_key + (size_t)warp * k, pe);
+        }
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s_next, 1);
+        s_ = __shfl_sync(0xffffffffu, nxt, 0);
+      }
+      if (hubs_shared) {
+        for (int s_ = 0; s_ < ns; ++s_) {
+          const int deg = s_deg[s_];
+          if (deg <= kHubDeg || deg <= k) continue;   // block-uniform
+          // every warp scans every 8th pass of 512 weights into its own reservoir ...
+          Res32 R;
+          if (warp == 0)
+            res32_init(R, s_w[s_], k, rng_key, (uint64_t)(i0 + s_), lane);
+          else
+            res32_empty(R, k, lane);
+          for (int t0 = (k & ~3) + 512 * warp; t0 < deg; t0 += 512 * kBkWarps)
+            res32_pass(R, s_w[s_], deg, k, t0, rng_key, (uint64_t)(i0 + s_), lane);
+          __syncthreads();   // the merge buffers of the previous hub are free
+          s_mkey[warp][lane] = R.rkey;
+          s_midx[warp][lane] = R.ridx;
+          __syncthreads();
+          // ... and warp 0 merges them: the k largest keys of the union
+          if (warp == 0) {
+            for (int w = 1; w < kBkWarps; ++w) {
+              const int ci = s_midx[w][lane];
+              res32_offer(R, (lane < k && ci >= 0) ? s_mkey[w][lane] : -INFINITY, ci, lane);
+            }
+            const int j = res32_rank(R, k, lane);
+            if (lane < k) s_pick[(size_t)s_ * k + j] = (unsigned int)R.ridx;
+          }
+        }
       }
     }
     __syncthreads();

@@ -81,6 +81,121 @@ __device__ __forceinline__ void emit_picks(const IdT *__restrict__ row, const in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// A-Res reservoir for k <= 32 (weighted sampling without replacement): the k largest keys
+// log2(u_t) / w_t, one slot per lane in REGISTERS - an insertion is a broadcast + a 5-step arg-min
+// butterfly, no shared-memory traffic.  Keys depend only on (rng_key, item, t), so the selected
+// SET does not depend on how the row is split over warps; the picks are emitted in descending
+// key order (ties: smaller position first), so neither does their order.  That lets a CTA share
+// one hub row among its warps (blocks.cu) and still agree with the one-warp-per-seed kernels.
+struct Res32 {
+  float rkey;   // this lane's slot; the slots are kept SORTED ascending over lanes 0..k-1
+                // (lanes >= k hold +inf), so the minimum is always lane 0 and an insertion is
+                // one ballot + one shift by a lane instead of an arg-min butterfly
+  int ridx;     // position inside the row, -1 = empty
+  float wmin;   // key of lane 0
+};
+
+__device__ __forceinline__ float ares_key(uint32_t r, float w) {
+  return w > 0.f ? __fdividef(__log2f(u32_to_unit(r)), w) : -INFINITY;
+}
+
+// empty reservoir (every real key replaces an empty slot)
+__device__ __forceinline__ void res32_empty(Res32 &R, int k, int lane) {
+  R.rkey = lane < k ? -INFINITY : INFINITY;
+  R.ridx = -1;
+  R.wmin = -INFINITY;
+}
+
+// reservoir holding the first k items of the row (bitonic sort of the 32 lanes)
+__device__ __forceinline__ void res32_init(Res32 &R, const float *__restrict__ wrow, int k,
+                                           uint64_t rng_key, uint64_t item, int lane) {
+  R.rkey = INFINITY;
+  R.ridx = 0;
+  if (lane < k) {
+    R.rkey = ares_key(philox_u32(rng_key, item, (uint32_t)lane), wrow[lane]);
+    R.ridx = lane;
+  }
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, R.rkey, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, R.ridx, stride);
+      const bool take_min = ((lane & stride) == 0) == ((lane & size) == 0);
+      const bool other_less = ok < R.rkey || (ok == R.rkey && oi < R.ridx);
+      const bool mine_less = R.rkey < ok || (R.rkey == ok && R.ridx < oi);
+      if (take_min ? other_less : mine_less) { R.rkey = ok; R.ridx = oi; }
+    }
+  }
+  R.wmin = __shfl_sync(0xffffffffu, R.rkey, 0);
+}
+
+// every lane offers one candidate (key, idx); those that beat the minimum enter, in lane order
+__device__ __forceinline__ void res32_offer(Res32 &R, float key, int idx, int lane) {
+  unsigned mask = __ballot_sync(0xffffffffu, key > R.wmin);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const float ck = __shfl_sync(0xffffffffu, key, src);
+    const int ci = __shfl_sync(0xffffffffu, idx, src);
+    if (ck > R.wmin) {  // warp-uniform
+      // slots below the candidate's place move down one lane (the minimum falls out)
+      const int pos = __popc(__ballot_sync(0xffffffffu, R.rkey < ck));   // >= 1
+      const float nk = __shfl_down_sync(0xffffffffu, R.rkey, 1);
+      const int ni = __shfl_down_sync(0xffffffffu, R.ridx, 1);
+      if (lane < pos - 1) { R.rkey = nk; R.ridx = ni; }
+      else if (lane == pos - 1) { R.rkey = ck; R.ridx = ci; }
+      R.wmin = __shfl_sync(0xffffffffu, R.rkey, 0);
+    }
+  }
+}
+
+// One pass over 512 weights starting at t0 (a multiple of 4; items below k are skipped - they
+// are in the initial reservoir): every lane owns 4 quads of 4 consecutive elements (quad q =
+// elements t0 + 128 q + 4 lane ..+3 = exactly one Philox block: draw t is component t & 3 of
+// block t >> 2, the same mapping as philox_u32).  All 16 weight loads of a lane are issued before
+// any is used - a hub row (deg ~ 10^4) is a chain of ~deg/512 memory round trips, not deg/32.
+__device__ __forceinline__ void res32_pass(Res32 &R, const float *__restrict__ wrow, int deg, int k,
+                                           int t0, uint64_t rng_key, uint64_t item, int lane) {
+  float w4[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int tb = t0 + 128 * q + 4 * lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int t = tb + c;
+      w4[q][c] = (t >= k && t < deg) ? wrow[t] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int tq = t0 + 128 * q;
+    if (tq >= deg) break;  // warp-uniform
+    const int tb = tq + 4 * lane;
+    float key4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (tb < deg) {
+      const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
+      const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) key4[c] = ares_key(rr[c], w4[q][c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) res32_offer(R, key4[c], tb + c, lane);
+  }
+}
+
+// output slot of this lane's pick: descending key, ties by ascending position
+__device__ __forceinline__ int res32_rank(const Res32 &R, int k, int lane) {
+  int rank = 0;
+  for (int l = 0; l < k; ++l) {
+    const float ok = __shfl_sync(0xffffffffu, R.rkey, l);
+    const int oi = __shfl_sync(0xffffffffu, R.ridx, l);
+    if (ok > R.rkey || (ok == R.rkey && oi < R.ridx)) ++rank;
+  }
+  return rank;
+}
+
 // One warp selects the neighbours of one seed and hands (output slot j, neighbour id) pairs to
 // `emit` (called by the lane that owns slot j).  copy_path: all `deg` neighbours in CSR order.
 // w_idx / w_key: per-warp scratch of k ints (+ k floats for kBias) when k > 32 or MODE == kBias.
@@ -143,72 +258,11 @@ __device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
     }
   } else if (MODE == kBias) {
     if (k <= 32) {
-      // reservoir of the k largest keys held one slot per lane in REGISTERS: an insertion is a
-      // broadcast + a 5-step arg-min butterfly, no shared-memory traffic
-      float rkey = INFINITY;   // lanes >= k never hold the minimum
-      int ridx = 0;
-      if (lane < k) {
-        const float w = wrow[lane];
-        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)lane));
-        rkey = w > 0.f ? __log2f(u) / w : -INFINITY;
-        ridx = lane;
-      }
-      float wmin = rkey;
-      int wslot = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-        const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-        if (ov < wmin || (ov == wmin && os < wslot)) { wmin = ov; wslot = os; }
-      }
-      for (int t0 = k & ~3; t0 < deg; t0 += 512) {
-        float w4[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int tb = t0 + 128 * q + 4 * lane;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int t = tb + c;
-            w4[q][c] = (t >= k && t < deg) ? wrow[t] : 0.f;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int tq = t0 + 128 * q;
-          if (tq >= deg) break;  // warp-uniform
-          const int tb = tq + 4 * lane;
-          float key4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (tb < deg) {
-            const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
-            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (w4[q][c] > 0.f) key4[c] = __log2f(u32_to_unit(rr[c])) / w4[q][c];
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float key = key4[c];
-            unsigned mask = __ballot_sync(0xffffffffu, key > wmin);
-            while (mask) {
-              const int src = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const float ck = __shfl_sync(0xffffffffu, key, src);
-              if (ck > wmin) {  // warp-uniform
-                if (lane == wslot) { rkey = ck; ridx = tq + 4 * src + c; }
-                wmin = rkey;
-                wslot = lane;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  const float ov = __shfl_xor_sync(0xffffffffu, wmin, o);
-                  const int os = __shfl_xor_sync(0xffffffffu, wslot, o);
-                  if (ov < wmin || (ov == wmin && os < wslot)) { wmin = ov; wslot = os; }
-                }
-              }
-            }
-          }
-        }
-      }
-      if (lane < k) emit(lane, pick_value<IdT, kPos>(row, ridx));
+      Res32 R;
+      res32_init(R, wrow, k, rng_key, item, lane);
+      for (int t0 = k & ~3; t0 < deg; t0 += 512) res32_pass(R, wrow, deg, k, t0, rng_key, item, lane);
+      const int j = res32_rank(R, k, lane);
+      if (lane < k) emit(j, pick_value<IdT, kPos>(row, R.ridx));
     } else {
       // fill the reservoir with the first k items
       for (int t = lane; t < k; t += 32) {

@@ -5,8 +5,9 @@ sys.path.insert(0, os.path.join(ROOT, "dist-gnn_b200"))
 import torch, dgs, dgs_synth
 dev = torch.device("cuda", 0)
 N, E, D, dt = dgs_synth.SHAPES["products"]
-ip, ix, _ = dgs_synth.make_csr(N, E, device=dev)
-sampler = dgs.classes.CSRSampler(ip, ix)
+BIAS = os.environ.get("BIAS", "0") == "1"
+ip, ix, pr = dgs_synth.make_csr(N, E, device=dev, weights=BIAS)
+sampler = dgs.classes.CSRSampler(ip, ix, pr if BIAS else None)
 B = int(os.environ.get("BATCH", "1024"))
 FAN = [int(x) for x in os.environ.get("FAN", "15,10,5").split(",")]
 seeds = dgs_synth.seed_batches(N, B, 12, device=dev)
