@@ -408,8 +408,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
   __shared__ int s_deg[kPkSeeds];
   __shared__ int s_cnt[kPkSeeds];
   __shared__ int s_next;                       // next seed of the tile to hand to a warp
-  __shared__ float s_mkey[kBkWarps][32];       // hub rows: per-warp reservoirs to merge
-  __shared__ int s_midx[kBkWarps][32];
+  __shared__ int s_mcount[kBkWarps];           // hub rows: finalists per warp
   unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
   float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -532,26 +531,25 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         for (int s_ = 0; s_ < ns; ++s_) {
           const int deg = s_deg[s_];
           if (deg <= kHubDeg || deg <= k) continue;   // block-uniform
-          // every warp scans every 8th pass of 512 weights into its own reservoir ...
-          Res32 R;
-          if (warp == 0)
-            res32_init(R, s_w[s_], k, rng_key, (uint64_t)(i0 + s_), lane);
-          else
-            res32_empty(R, k, lane);
-          for (int t0 = (k & ~3) + 512 * warp; t0 < deg; t0 += 512 * kBkWarps)
-            res32_pass(R, s_w[s_], deg, k, t0, rng_key, (uint64_t)(i0 + s_), lane);
-          __syncthreads();   // the merge buffers of the previous hub are free
-          s_mkey[warp][lane] = R.rkey;
-          s_midx[warp][lane] = R.ridx;
+          // every warp scans every 8th pass of 512 weights into its own candidate list ...
+          __syncthreads();   // the lists of the previous hub row have been read
+          const AresBuf mine = ares_buf(warp);
+          const int M = ares_collect(s_w[s_], deg, k, 512 * warp, 512 * kBkWarps, rng_key,
+                                     (uint64_t)(i0 + s_), lane, mine);
+          if (lane == 0) s_mcount[warp] = M;
           __syncthreads();
-          // ... and warp 0 merges them: the k largest keys of the union
-          if (warp == 0) {
-            for (int w = 1; w < kBkWarps; ++w) {
-              const int ci = s_midx[w][lane];
-              res32_offer(R, (lane < k && ci >= 0) ? s_mkey[w][lane] : -INFINITY, ci, lane);
+          // ... and every finalist counts how many finalists of all warps beat it: the k best of
+          // the union, in order
+          if (lane < M) {
+            const float kv = mine.key[lane];
+            const int iv = mine.idx[lane];
+            int rank = 0;
+            for (int w = 0; w < kBkWarps; ++w) {
+              const AresBuf o = ares_buf(w);
+              const int Mo = s_mcount[w];
+              for (int j = 0; j < Mo; ++j) rank += ares_before(o.key[j], o.idx[j], kv, iv) ? 1 : 0;
             }
-            const int j = res32_rank(R, k, lane);
-            if (lane < k) s_pick[(size_t)s_ * k + j] = (unsigned int)R.ridx;
+            if (rank < k) s_pick[(size_t)s_ * k + rank] = (unsigned int)iv;
           }
         }
       }

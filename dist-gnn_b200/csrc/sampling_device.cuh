@@ -82,118 +82,153 @@ __device__ __forceinline__ void emit_picks(const IdT *__restrict__ row, const in
 }
 
 // ---------------------------------------------------------------------------------------------
-// A-Res reservoir for k <= 32 (weighted sampling without replacement): the k largest keys
-// log2(u_t) / w_t, one slot per lane in REGISTERS - an insertion is a broadcast + a 5-step arg-min
-// butterfly, no shared-memory traffic.  Keys depend only on (rng_key, item, t), so the selected
-// SET does not depend on how the row is split over warps; the picks are emitted in descending
-// key order (ties: smaller position first), so neither does their order.  That lets a CTA share
-// one hub row among its warps (blocks.cu) and still agree with the one-warp-per-seed kernels.
-struct Res32 {
-  float rkey;   // this lane's slot; the slots are kept SORTED ascending over lanes 0..k-1
-                // (lanes >= k hold +inf), so the minimum is always lane 0 and an insertion is
-                // one ballot + one shift by a lane instead of an arg-min butterfly
-  int ridx;     // position inside the row, -1 = empty
-  float wmin;   // key of lane 0
+// A-Res for k <= 32 (weighted sampling without replacement = the k largest keys log2(u_t) / w_t).
+// A reservoir that replaces its minimum item by item is a chain of ~k ln(deg / k) DEPENDENT warp
+// operations per row (measured: ~10 us for a 512-weight row, 25 picks).  Instead:
+//   * threshold: after the first 512 weights, tau = the k-th largest of the 32 per-lane maxima -
+//     a lower bound of the k-th largest key, found with one round of shuffles;
+//   * collect: every later key above tau is appended to a per-warp candidate list in shared
+//     memory (ballot + popc, no dependence between candidates);
+//   * tighten: when the list fills up (and at the end) every candidate counts how many others
+//     beat it - all comparisons independent - and the k best move to the front IN ORDER, which
+//     also yields the exact new tau.
+// Keys depend only on (rng_key, item, t) and the order is total (key descending, ties by
+// position), so neither the selected set nor the order of the picks depends on how a row is split
+// over warps: a CTA can share a hub row (blocks.cu) and still agree with the one-warp kernels.
+// The picks come out in descending key order, as in the reference (rowwise_sampling_bias.cu:127).
+constexpr int kAresCap = 128;   // candidates per warp
+
+struct AresBuf {
+  float *key;
+  int *idx;
 };
+
+// candidate list of warp w of this CTA (all callers run 8 warps per CTA)
+__device__ __forceinline__ AresBuf ares_buf(int w) {
+  __shared__ float s_ck[8][kAresCap];
+  __shared__ int s_ci[8][kAresCap];
+  return AresBuf{s_ck[w], s_ci[w]};
+}
 
 __device__ __forceinline__ float ares_key(uint32_t r, float w) {
   return w > 0.f ? __fdividef(__log2f(u32_to_unit(r)), w) : -INFINITY;
 }
 
-// empty reservoir (every real key replaces an empty slot)
-__device__ __forceinline__ void res32_empty(Res32 &R, int k, int lane) {
-  R.rkey = lane < k ? -INFINITY : INFINITY;
-  R.ridx = -1;
-  R.wmin = -INFINITY;
+// candidate a is picked before candidate b
+__device__ __forceinline__ bool ares_before(float ka, int ia, float kb, int ib) {
+  return ka > kb || (ka == kb && ia < ib);
 }
 
-// reservoir holding the first k items of the row (bitonic sort of the 32 lanes)
-__device__ __forceinline__ void res32_init(Res32 &R, const float *__restrict__ wrow, int k,
-                                           uint64_t rng_key, uint64_t item, int lane) {
-  R.rkey = INFINITY;
-  R.ridx = 0;
-  if (lane < k) {
-    R.rkey = ares_key(philox_u32(rng_key, item, (uint32_t)lane), wrow[lane]);
-    R.ridx = lane;
+// Keep the k best of the M listed candidates at the front of the list, best first.
+// Returns min(M, k); tau = the k-th key when there are at least k.
+__device__ __forceinline__ int ares_tighten(const AresBuf &b, int M, int k, int lane, float &tau) {
+  __syncwarp();
+  float kk[kAresCap / 32];
+  int ii[kAresCap / 32], rk[kAresCap / 32];
+#pragma unroll
+  for (int r = 0; r < kAresCap / 32; ++r) {
+    const int e = lane + 32 * r;
+    kk[r] = e < M ? b.key[e] : -INFINITY;
+    ii[r] = e < M ? b.idx[e] : 0x7fffffff;
+    rk[r] = 0;
   }
+  for (int j = 0; j < M; ++j) {
+    const float kj = b.key[j];   // broadcast reads
+    const int ij = b.idx[j];
 #pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
+    for (int r = 0; r < kAresCap / 32; ++r) rk[r] += ares_before(kj, ij, kk[r], ii[r]) ? 1 : 0;
+  }
+  __syncwarp();
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const float ok = __shfl_xor_sync(0xffffffffu, R.rkey, stride);
-      const int oi = __shfl_xor_sync(0xffffffffu, R.ridx, stride);
-      const bool take_min = ((lane & stride) == 0) == ((lane & size) == 0);
-      const bool other_less = ok < R.rkey || (ok == R.rkey && oi < R.ridx);
-      const bool mine_less = R.rkey < ok || (R.rkey == ok && R.ridx < oi);
-      if (take_min ? other_less : mine_less) { R.rkey = ok; R.ridx = oi; }
+  for (int r = 0; r < kAresCap / 32; ++r) {
+    if (lane + 32 * r < M && rk[r] < k) {
+      b.key[rk[r]] = kk[r];
+      b.idx[rk[r]] = ii[r];
     }
   }
-  R.wmin = __shfl_sync(0xffffffffu, R.rkey, 0);
+  __syncwarp();
+  if (M >= k) tau = b.key[k - 1];
+  return min(M, k);
 }
 
-// every lane offers one candidate (key, idx); those that beat the minimum enter, in lane order
-__device__ __forceinline__ void res32_offer(Res32 &R, float key, int idx, int lane) {
-  unsigned mask = __ballot_sync(0xffffffffu, key > R.wmin);
-  while (mask) {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const float ck = __shfl_sync(0xffffffffu, key, src);
-    const int ci = __shfl_sync(0xffffffffu, idx, src);
-    if (ck > R.wmin) {  // warp-uniform
-      // slots below the candidate's place move down one lane (the minimum falls out)
-      const int pos = __popc(__ballot_sync(0xffffffffu, R.rkey < ck));   // >= 1
-      const float nk = __shfl_down_sync(0xffffffffu, R.rkey, 1);
-      const int ni = __shfl_down_sync(0xffffffffu, R.ridx, 1);
-      if (lane < pos - 1) { R.rkey = nk; R.ridx = ni; }
-      else if (lane == pos - 1) { R.rkey = ck; R.ridx = ci; }
-      R.wmin = __shfl_sync(0xffffffffu, R.rkey, 0);
-    }
-  }
-}
-
-// One pass over 512 weights starting at t0 (a multiple of 4; items below k are skipped - they
-// are in the initial reservoir): every lane owns 4 quads of 4 consecutive elements (quad q =
-// elements t0 + 128 q + 4 lane ..+3 = exactly one Philox block: draw t is component t & 3 of
-// block t >> 2, the same mapping as philox_u32).  All 16 weight loads of a lane are issued before
-// any is used - a hub row (deg ~ 10^4) is a chain of ~deg/512 memory round trips, not deg/32.
-__device__ __forceinline__ void res32_pass(Res32 &R, const float *__restrict__ wrow, int deg, int k,
-                                           int t0, uint64_t rng_key, uint64_t item, int lane) {
-  float w4[4][4];
+// Scan the passes t_begin, t_begin + t_stride, ... (512 weights each; t_begin a multiple of 512)
+// of one row and leave the (up to k) best candidates among them at the front of the warp's list,
+// best first.  Every lane owns 4 quads of 4 consecutive elements per pass (quad q = elements
+// t0 + 128 q + 4 lane ..+3 = exactly one Philox block: draw t is component t & 3 of block t >> 2,
+// the mapping of philox_u32); all 16 weight loads of a lane are issued before any is used.
+__device__ __forceinline__ int ares_collect(const float *__restrict__ wrow, int deg, int k,
+                                            int t_begin, int t_stride, uint64_t rng_key,
+                                            uint64_t item, int lane, const AresBuf &b) {
+  int M = 0;
+  float tau = -INFINITY;
+  bool strict = false;   // false until tau is an exact k-th key: candidates equal to tau still count
+  for (int t0 = t_begin; t0 < deg; t0 += t_stride) {
+    float key[4][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int tb = t0 + 128 * q + 4 * lane;
+    for (int q = 0; q < 4; ++q) {
+      const int tb = t0 + 128 * q + 4 * lane;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int t = tb + c;
-      w4[q][c] = (t >= k && t < deg) ? wrow[t] : 0.f;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int tq = t0 + 128 * q;
-    if (tq >= deg) break;  // warp-uniform
-    const int tb = tq + 4 * lane;
-    float key4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    if (tb < deg) {
-      const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
-      const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) key4[c] = ares_key(rr[c], w4[q][c]);
+      for (int c = 0; c < 4; ++c) key[q][c] = (tb + c < deg) ? wrow[tb + c] : 0.f;   // weights first
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) res32_offer(R, key4[c], tb + c, lane);
+    for (int q = 0; q < 4; ++q) {
+      const int tb = t0 + 128 * q + 4 * lane;
+      if (tb < deg) {
+        const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)(tb >> 2));
+        key[q][0] = ares_key(r4.x, key[q][0]);
+        key[q][1] = ares_key(r4.y, key[q][1]);
+        key[q][2] = ares_key(r4.z, key[q][2]);
+        key[q][3] = ares_key(r4.w, key[q][3]);
+      } else {
+        key[q][0] = key[q][1] = key[q][2] = key[q][3] = -INFINITY;
+      }
+    }
+    if (t0 == t_begin) {
+      // lower bound of the k-th largest key: the k-th largest of the 32 per-lane maxima
+      float m = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m = fmaxf(m, key[q][c]);
+      int rank = 0;
+      for (int l = 0; l < 32; ++l) {
+        const float o = __shfl_sync(0xffffffffu, m, l);
+        rank += (o > m || (o == m && l < lane)) ? 1 : 0;
+      }
+      const unsigned has = __ballot_sync(0xffffffffu, rank == k - 1);
+      tau = __shfl_sync(0xffffffffu, m, __ffs(has) - 1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (t0 + 128 * q >= deg) break;   // warp-uniform
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int t = t0 + 128 * q + 4 * lane + c;
+        const float kv = key[q][c];
+        const bool pred = t < deg && (strict ? kv > tau : kv >= tau);
+        const unsigned mask = __ballot_sync(0xffffffffu, pred);
+        if (mask) {
+          if (pred) {
+            const int pos = M + __popc(mask & ((1u << lane) - 1));
+            b.key[pos] = kv;
+            b.idx[pos] = t;
+          }
+          M += __popc(mask);
+          if (M > kAresCap - 32) {   // no room for another column: keep the k best
+            const int had = M;
+            M = ares_tighten(b, M, k, lane, tau);
+            strict = strict || had >= k;
+          }
+        }
+      }
+    }
+    if (M >= k && (!strict || M > 2 * k)) {   // exact tau as soon as k candidates exist
+      M = ares_tighten(b, M, k, lane, tau);
+      strict = true;
+    }
   }
-}
-
-// output slot of this lane's pick: descending key, ties by ascending position
-__device__ __forceinline__ int res32_rank(const Res32 &R, int k, int lane) {
-  int rank = 0;
-  for (int l = 0; l < k; ++l) {
-    const float ok = __shfl_sync(0xffffffffu, R.rkey, l);
-    const int oi = __shfl_sync(0xffffffffu, R.ridx, l);
-    if (ok > R.rkey || (ok == R.rkey && oi < R.ridx)) ++rank;
-  }
-  return rank;
+  float unused;
+  return ares_tighten(b, M, k, lane, unused);
 }
 
 // One warp selects the neighbours of one seed and hands (output slot j, neighbour id) pairs to
@@ -258,11 +293,10 @@ __device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
     }
   } else if (MODE == kBias) {
     if (k <= 32) {
-      Res32 R;
-      res32_init(R, wrow, k, rng_key, item, lane);
-      for (int t0 = k & ~3; t0 < deg; t0 += 512) res32_pass(R, wrow, deg, k, t0, rng_key, item, lane);
-      const int j = res32_rank(R, k, lane);
-      if (lane < k) emit(j, pick_value<IdT, kPos>(row, R.ridx));
+      const AresBuf b = ares_buf(threadIdx.x >> 5);
+      const int M = ares_collect(wrow, deg, k, 0, 512, rng_key, item, lane, b);   // M == k (deg > k)
+      if (lane < M) emit(lane, pick_value<IdT, kPos>(row, b.idx[lane]));
+      __syncwarp();
     } else {
       // fill the reservoir with the first k items
       for (int t = lane; t < k; t += 32) {
