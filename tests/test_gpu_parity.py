@@ -597,6 +597,31 @@ print(h.hexdigest())
     assert digests[0] == digests[1]
 
 
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("bias", [False, True])
+def test_fused_blocks_equal_per_hop_ops(dgs, cuda, bias, replace):
+    """The fused whole-batch kernel (tile phases: thread-per-seed Floyd in registers, CTA-shared hub
+    rows for weighted sampling) and the per-hop ops (plan + warp-per-seed pick + relabel op) draw
+    from the same Philox counters: with the same seed every hop must be identical, tensor by
+    tensor - on a graph whose degrees reach past the 512-weight hub threshold and the fan-outs
+    cover k <= 16, 16 < k <= 32 and k > 32."""
+    N = 12000
+    indptr, indices, probs = dgs_synth.make_csr(N, 1500000, seed=61, weights=bias)
+    deg = indptr[1:] - indptr[:-1]
+    assert int(deg.max()) > 4096 and int((deg > 512).sum()) > 20
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda), probs.to(cuda) if bias else None)
+    hubs = torch.argsort(deg, descending=True)[:40]
+    seeds = torch.unique(torch.cat([hubs, torch.randperm(N, generator=torch.Generator().manual_seed(3))[:400]]))
+    seeds = seeds[torch.randperm(seeds.numel(), generator=torch.Generator().manual_seed(4))].to(cuda)
+    for fan in ([12, 5], [25, 10], [40]):
+        a = smp._pipe.sample(seeds, fan, replace, 777)
+        b = smp._pipe._sample_per_hop(seeds, fan, replace, 777)
+        assert len(a) == len(b) == len(fan)
+        for x, y in zip(a, b):
+            for u, v in zip(x, y):
+                assert torch.equal(u, v)
+
+
 @pytest.mark.parametrize("idt", [torch.int64, torch.int32])
 @pytest.mark.parametrize("bias", [False, True])
 def test_fused_blocks_direct_equals_hashed_tables(dgs, cuda, idt, bias):
