@@ -719,13 +719,68 @@ __device__ __forceinline__ void rank_tail(int64_t S, const BlocksWs &ws, long lo
   }
 }
 
+// Where the exclusive per-tile prefixes live during the emit phase: in global memory (written by
+// the last-CTA tail; multi-kernel path) or in the CTA's own shared memory (cooperative kernel:
+// every CTA scans the per-tile totals itself right after the barrier - no atomic counter, no
+// serial tail, and the emit's prefix lookups never leave the SM).
+struct TilePrefix {
+  const long long *gA, *gB, *gC;       // global
+  const unsigned int *sA, *sB, *sC;    // shared (non-null selects them)
+  __device__ __forceinline__ long long A(int64_t t) const { return sA ? (long long)sA[t] : ldcg(gA + t); }
+  __device__ __forceinline__ long long B(int64_t t) const { return sB ? (long long)sB[t] : ldcg(gB + t); }
+  __device__ __forceinline__ long long C(int64_t t) const { return sC ? (long long)sC[t] : ldcg(gC + t); }
+};
+
 // new id of the key stored in `s` (first occurrence f, rank inside its tile)
 __device__ __forceinline__ long long new_id(const RlSlot &s, int64_t S_ub, int k, long long totA,
-                                            const long long *prefA, const long long *prefB) {
+                                            const TilePrefix &pf, bool unique_seeds) {
   const unsigned int f = s.first;
-  if ((int64_t)f < S_ub) return ldcg(prefA + f / kBkTile) + (long long)s.lrank;
+  if ((int64_t)f < S_ub) return unique_seeds ? (long long)f : pf.A(f / kBkTile) + (long long)s.lrank;
   const int64_t e = (int64_t)f - S_ub;
-  return totA + ldcg(prefB + (e / k) / kBkTile) + (long long)s.lrank;
+  return totA + pf.B((e / k) / kBkTile) + (long long)s.lrank;
+}
+
+// Cooperative kernel, start of the emit phase: exclusive scans of the per-tile totals (ws.prefA/B/C
+// hold TOTALS here) into shared memory; CTA 0 publishes nnz and |frontier|.  Entries [0, tiles].
+__device__ __forceinline__ void scan_totals_to_smem(int64_t S, const BlocksWs &ws, bool unique_seeds,
+                                                    unsigned int *sA, unsigned int *sB,
+                                                    unsigned int *sC, long long *out_nnz,
+                                                    long long *out_nfront) {
+  __shared__ long long t_scan[32];
+  __shared__ long long t_total;
+  const int tid = threadIdx.x;
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  const int64_t per = (tiles + kBkThreads - 1) / kBkThreads;
+  const int64_t t0 = min(tiles, (int64_t)tid * per), t1 = min(tiles, t0 + per);
+  long long sa = 0, sbc = 0;   // B in the high half, C in the low half (both < 2^32)
+  for (int64_t t = t0; t < t1; ++t) {
+    if (!unique_seeds) sa += ldcg(ws.prefA + t);
+    sbc += (ldcg(ws.prefB + t) << 32) | ldcg(ws.prefC + t);
+  }
+  long long xbc = block_exclusive_scan<long long>(sbc, t_scan, &t_total);
+  const long long totBC = t_total;
+  long long xa = 0, totA = S;
+  if (!unique_seeds) {
+    xa = block_exclusive_scan<long long>(sa, t_scan, &t_total);
+    totA = t_total;
+  }
+  for (int64_t t = t0; t < t1; ++t) {
+    sA[t] = unique_seeds ? (unsigned int)(t * kBkTile) : (unsigned int)xa;
+    sB[t] = (unsigned int)(xbc >> 32);
+    sC[t] = (unsigned int)(xbc & 0xffffffffll);
+    if (!unique_seeds) xa += ldcg(ws.prefA + t);
+    xbc += (ldcg(ws.prefB + t) << 32) | ldcg(ws.prefC + t);
+  }
+  if (tid == 0) {
+    sA[tiles] = (unsigned int)totA;
+    sB[tiles] = (unsigned int)(totBC >> 32);
+    sC[tiles] = (unsigned int)(totBC & 0xffffffffll);
+    if (blockIdx.x == 0) {
+      *out_nnz = totBC & 0xffffffffll;
+      *out_nfront = totA + (totBC >> 32);
+    }
+  }
+  __syncthreads();
 }
 
 // Emit phase: thread per padded slot - frontier[new id] = id for first occurrences, COO written
@@ -735,9 +790,10 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
                                            int k, const IdT *__restrict__ pad_col,
                                            const HopState &cur, const BlocksWs &ws,
                                            IdT *__restrict__ frontier, IdT *__restrict__ out_row,
-                                           IdT *__restrict__ out_col, bool unique_seeds) {
+                                           IdT *__restrict__ out_col, bool unique_seeds,
+                                           const TilePrefix &pf) {
   const int64_t tiles = (S + kBkTile - 1) / kBkTile;
-  const long long totA = ldcg(ws.prefA + tiles);
+  const long long totA = pf.A(tiles);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) *ws.pending_S = S;  // this hop's table is dirty until the next pick phase wipes it
@@ -747,7 +803,7 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
     for (int64_t i = tid; i < S; i += stride) {
       const int2 fl = cur.table.first_lrank(ldcg(cur.pos_seed + i));
       if ((unsigned int)fl.x == (unsigned int)i)
-        frontier[ldcg(ws.prefA + i / kBkTile) + (long long)(unsigned int)fl.y] = ldcg(seeds + i);
+        frontier[pf.A(i / kBkTile) + (long long)(unsigned int)fl.y] = ldcg(seeds + i);
     }
   }
   if (k <= 0) return;
@@ -788,11 +844,11 @@ __device__ __forceinline__ void emit_phase(const IdT *__restrict__ seeds, int64_
         RlSlot sc;
         sc.first = cf[u];
         sc.lrank = cr[u];
-        const long long cid = new_id(sc, S_ub, k, totA, ws.prefA, ws.prefB);
+        const long long cid = new_id(sc, S_ub, k, totA, pf, unique_seeds);
         if ((int64_t)cf[u] == S_ub + e) frontier[cid] = ldcg(pad_col + e);
         const long long rid =
-            unique_seeds ? (long long)si[u] : ldcg(ws.prefA + sf[u] / kBkTile) + (long long)sr[u];
-        const long long o = ldcg(ws.prefC + si[u] / kBkTile) + (long long)ldcg(ws.loff + si[u]) + jj[u];
+            unique_seeds ? (long long)si[u] : pf.A(sf[u] / kBkTile) + (long long)sr[u];
+        const long long o = pf.C(si[u] / kBkTile) + (long long)ldcg(ws.loff + si[u]) + jj[u];
         out_row[o] = (IdT)rid;
         out_col[o] = (IdT)cid;
       }
@@ -843,7 +899,8 @@ fused_emit_kernel(const IdT *__restrict__ seeds, int64_t S_ub, const int64_t *__
                   IdT *__restrict__ frontier, IdT *__restrict__ out_row, IdT *__restrict__ out_col,
                   int unique_seeds) {
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
-  emit_phase<IdT>(seeds, S_ub, S, k, pad_col, cur, ws, frontier, out_row, out_col, unique_seeds != 0);
+  const TilePrefix pf{ws.prefA, ws.prefB, ws.prefC, nullptr, nullptr, nullptr};
+  emit_phase<IdT>(seeds, S_ub, S, k, pad_col, cur, ws, frontier, out_row, out_col, unique_seeds != 0, pf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -858,6 +915,7 @@ struct HopArgs {
   int64_t S_ub, prev_S_ub;
   uint64_t key;
   int k, prev_k, cur;
+  int smem_pref;   // emit phase keeps the tile prefixes in shared memory (they fit)
 };
 struct BatchArgs {
   int L;
@@ -895,7 +953,20 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     stamp();
     rank_tiles_phase(h.S_ub, S, h.k, cur, ws, l > 0);
     stamp();
-    {
+    TilePrefix pf{ws.prefA, ws.prefB, ws.prefC, nullptr, nullptr, nullptr};
+    if (h.smem_pref) {
+      stamp();
+      grid.sync();
+      stamp();
+      extern __shared__ __align__(16) unsigned char dyn_smem[];
+      const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+      unsigned int *sA = reinterpret_cast<unsigned int *>(dyn_smem);
+      unsigned int *sB = sA + (tiles + 1), *sC = sB + (tiles + 1);
+      scan_totals_to_smem(S, ws, l > 0, sA, sB, sC, h.nnz_dev, h.nf_dev);
+      pf.sA = sA;
+      pf.sB = sB;
+      pf.sC = sC;
+    } else {
       __shared__ bool s_last;
       __threadfence();
       __syncthreads();
@@ -906,12 +977,12 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
         rank_tail(S, ws, h.nnz_dev, h.nf_dev);
         if (threadIdx.x == 0) *ws.done = 0;
       }
+      stamp();
+      grid.sync();
+      stamp();
     }
-    stamp();
-    grid.sync();
-    stamp();
     emit_phase<IdT>((const IdT *)h.seeds, h.S_ub, S, h.k, (const IdT *)ws.pad_col, cur, ws,
-                    (IdT *)h.frontier, (IdT *)h.out_row, (IdT *)h.out_col, l > 0);
+                    (IdT *)h.frontier, (IdT *)h.out_row, (IdT *)h.out_col, l > 0, pf);
     stamp();
     grid.sync();
     stamp();
@@ -992,6 +1063,10 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
       h.k = (int)fan_out[L - 1 - l];
       h.prev_k = (int)fan_out[L - 1 - pl];
       h.cur = (int)((epoch * L + l) & 1);
+      const size_t pref_bytes = 3 * ((size_t)(ubs[l] + kBkTile - 1) / kBkTile + 1) * sizeof(unsigned int);
+      static const bool no_smem_pref = getenv("DGS_BLOCKS_GLOBAL_PREFIX") != nullptr;
+      h.smem_pref = (!no_smem_pref && pref_bytes <= 64 * 1024) ? 1 : 0;
+      if (h.smem_pref && pref_bytes > smem_max) smem_max = pref_bytes;
     }
     void *kern = nullptr;
 #define DGS_BK(M) kern = (void *)fused_batch_kernel<IdT, ET, M>
