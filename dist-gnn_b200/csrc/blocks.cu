@@ -7,20 +7,22 @@
 // the sampling kernel, 2 torch::cat, 3 torch::full of the hash size, 4 thrust relabel passes,
 // 2 more scan kernels) and block twice on a D2H read (rowwise_sampling_p2p.cu:226-228,
 // tensor_relabel.cu:129).  At batch 1024 every one of those kernels is a few microseconds, so the
-// reference's hop is launch- and sync-bound (measured on B200: 0.72 ms per 3-hop batch vs 0.15 ms
-// here); a hop here is three dependent phases separated by grid barriers:
+// reference's hop is launch- and sync-bound (measured on B200: 0.70 ms per 3-hop batch vs 0.14 ms
+// here, host sync included); a hop here is three dependent phases separated by grid barriers:
 //
 //   pick  : CTA per <= 128 seeds.  Location probe, indptr pair from the owner (local HBM / NVLink
 //           peer / pinned host), selection (sampling_device.cuh), neighbours written to a PADDED
 //           slot array (seed i owns slots [i k, (i+1) k)) - so no prefix sum is needed before
 //           sampling - and every seed / neighbour id is inserted on the fly into the hop's
-//           relabel table (CAS on the key, atomicMin on the item index = first occurrence).
-//           Idle CTAs wipe the slots the previous hop touched in the other table (two alternate),
-//           so no memset ever runs.
+//           relabel table: atomicMin of the item index = first occurrence, at slot = node id when
+//           the node count is known (direct table, struct Tab), else after a CAS on the key of a
+//           hashed slot.  Idle CTAs wipe the slots the previous hop touched in the other table
+//           (two alternate), so no memset ever runs.
 //   rank  : CTA per 128 seeds.  Flags first occurrences among the seeds (A) and among the sampled
-//           neighbours (B), counts the edges (C), block scans; the last CTA to finish turns the
-//           three per-tile totals into exclusive prefixes and publishes nnz = C and
-//           |frontier| = A + B on the device.
+//           neighbours (B), counts the edges (C), block scans -> per-tile totals.  The totals
+//           become exclusive prefixes in every CTA's shared memory at the start of the emit phase
+//           (cooperative kernel) or through the last CTA to finish (multi-kernel path); nnz = C
+//           and |frontier| = A + B are published on the device.
 //   emit  : thread per padded slot.  frontier[new id] = id for first occurrences, and the COO is
 //           written compacted and relabelled: row = new id of the seed, col = new id of the
 //           neighbour (new id = tile prefix + rank inside the tile).
