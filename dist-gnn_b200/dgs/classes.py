@@ -270,7 +270,10 @@ class _BlockPipeline:
                           a_col=(C.c_void_p * L)(), count_slots=2 * L * 8 // es,
                           counts_host=counts_host, counts_np=counts_host.numpy(),
                           counts_ptr=counts_host.data_ptr())
-            if len(self._plans) > 8:
+            # workspaces are cached per (batch, fan-out); with direct-addressed relabel tables one
+            # holds 16 bytes per graph node, so keep fewer of them when they are large
+            big = pl["ws"] is not None and pl["ws_bytes"] > (1 << 30)
+            if len(self._plans) >= (2 if big else 8):
                 self._plans.clear()
             self._plans[key] = pl
         return pl
