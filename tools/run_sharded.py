@@ -26,6 +26,10 @@ from DistGNN.dist import create_communicator  # noqa: E402
 
 
 def main():
+    # only the JSON object goes to stdout: libraries (NCCL's version banner) write to fd 1 as well
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="papers100M")
     ap.add_argument("--batch", type=int, default=1024)
@@ -158,7 +162,7 @@ def main():
     del keep
     if rank == 0:
         R = args.extract_rows
-        print(json.dumps({
+        os.write(json_fd, (json.dumps({
             "shape": args.shape, "n_gpus": world, "batch": args.batch, "fan_out": fan,
             "bias": args.bias, "replicate_hot": args.replicate_hot, "hot_rows_replicated_per_gpu": hot_extra,
             "loc_mode": "modulo" if fs._mod_world else "hash", "gen_s": t_gen, "build_s": t_build,
@@ -175,7 +179,7 @@ def main():
                              "algorithmic_gbps_per_gpu": R * (2 * row_bytes + 8) / (xms * 1e-3) / 1e9,
                              "peer_load_gbps_per_gpu": R * row_bytes * (world - 1) / world / (xms * 1e-3) / 1e9,
                              "nvlink_peak_gbps": 900, "nvlink_measured_peer_copy_gbps": 770},
-            "mem_allocated_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+            "mem_allocated_gb": torch.cuda.max_memory_allocated() / 1e9}) + "\n").encode())
     if world > 1:
         dist.barrier()
     smp.close(barrier=False)
