@@ -923,6 +923,7 @@ struct BatchArgs {
   int L;
   uint64_t cap_mask;
   unsigned long long *trace;  // debug: %globaltimer stamps of CTA 0 around every phase
+  long long *host_counts;     // mapped pinned host memory for the 2 L hop sizes (or null)
   HopArgs hop[8];
 };
 
@@ -989,6 +990,15 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     grid.sync();
     stamp();
   }
+  // The hop sizes go straight into the caller's pinned host memory (posted PCIe writes): entry 0
+  // is written last, behind a system-scope fence, and is what the host polls - no copy engine,
+  // no stream synchronisation in the one host round trip of a batch.
+  if (a.host_counts != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long *dev = a.hop[0].nnz_dev;   // {nnz_0, |frontier_0|, nnz_1, ...}
+    for (int i = 1; i < 2 * a.L; ++i) a.host_counts[i] = ldcg(dev + i);
+    __threadfence_system();
+    *(volatile long long *)a.host_counts = ldcg(dev);
+  }
 }
 
 __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {
@@ -1004,7 +1014,9 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
                          const int64_t *fan_out, int replace, uint64_t rng_seed, int64_t epoch,
                          void *const *out_frontier, void *const *out_row, void *const *out_col,
                          const int64_t *cap_edges, const int64_t *cap_frontier,
-                         int64_t *counts_dev, const BlocksWs &ws, cudaStream_t st) {
+                         int64_t *counts_dev, const BlocksWs &ws, cudaStream_t st,
+                         long long *host_counts, bool *host_counts_used) {
+  *host_counts_used = false;
   const bool bias = src.probs != nullptr || src.sh_probs.p[0] != nullptr;
   const int mode = bias ? (replace ? kBiasReplace : kBias) : (replace ? kUniformReplace : kUniform);
   const uint64_t cap_mask = (uint64_t)ws.cap - 1;
@@ -1092,6 +1104,8 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
       static unsigned long long *trace_dev = nullptr;
       if (trace && !trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(unsigned long long));
       a.trace = trace ? trace_dev : nullptr;
+      a.host_counts = host_counts;
+      *host_counts_used = host_counts != nullptr;
       void *params[] = {&src_copy, &ws_copy, &a};
       DGS_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kBkThreads), params, smem_max, st));
       dgsb::g_launches += 1;
@@ -1288,17 +1302,51 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
               (long long)ws_bytes, (long long)p.bytes);
   GraphSrc src;
   if (build_graph_src(g, &src)) return 1;
+  // Can the kernel write the hop sizes into counts_host itself?  (pinned + mapped host memory;
+  // the answer is remembered for the last pointer asked about)
+  long long *host_dev = nullptr;
+  if (counts_host) {
+    static const bool no_direct = getenv("DGS_BLOCKS_COUNTS_MEMCPY") != nullptr;
+    static int64_t *last_host = nullptr;
+    static long long *last_dev = nullptr;
+    if (!no_direct) {
+      if (counts_host != last_host) {
+        cudaPointerAttributes at;
+        void *dp = nullptr;
+        if (cudaPointerGetAttributes(&at, counts_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&dp, counts_host, 0) == cudaSuccess)
+          last_dev = (long long *)dp;
+        else
+          last_dev = nullptr;
+        cudaGetLastError();
+        last_host = counts_host;
+      }
+      host_dev = last_dev;
+    }
+    if (host_dev) *(volatile int64_t *)counts_host = -1;   // sentinel: hop sizes are >= 0
+  }
   int rc = 0;
+  bool by_kernel = false;
   DGS_ITYPE_SWITCH(g->itype, IdT, {
     DGS_ITYPE_SWITCH(g->etype, ET, {
       rc = launch_blocks<IdT, ET>(src, (const IdT *)seeds, num_seeds, num_layers, fan_out, replace,
                                   rng_seed, epoch, out_frontier, out_row, out_col, cap_edges,
-                                  cap_frontier, counts_dev, w, st);
+                                  cap_frontier, counts_dev, w, st, host_dev, &by_kernel);
     });
   });
   if (rc) return rc;
   if (counts_host) {
     // the one host round trip of the batch: hop sizes -> (pinned) host memory
+    if (by_kernel) {
+      volatile int64_t *flag = counts_host;
+      unsigned int spins = 0;
+      while (*flag == -1) {
+        if ((++spins & 0x3ffu) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;
+      }
+      if (*flag != -1) return 0;
+      // the stream drained (or failed) without the sizes arriving: take the copy path, which also
+      // reports a kernel fault
+    }
     DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * num_layers,
                                 cudaMemcpyDeviceToHost, st));
     DGS_CUDA_OK(cudaStreamSynchronize(st));

@@ -207,8 +207,13 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
  * dirty is wiped by the first kernel of the next call, which needs to know which of the two
  * alternating tables that is.  One cooperative launch per batch (or 3 kernels per hop when the
  * fan-out is too large for the tile kernels), no memset, no trailing clean-up launch.
- * counts_host (optional, pinned host memory, 2 L int64): when non-NULL the counts are copied back
- * and the stream is synchronised before returning - the single host round trip of a batch. */
+ * counts_host (optional, pinned host memory, 2 L int64): when non-NULL the call returns once the
+ * counts have arrived there - the single host round trip of a batch.  If the memory is mapped
+ * into the device's address space (cudaHostAlloc / cudaHostRegister under UVA) the cooperative
+ * kernel writes the counts itself and the host polls for them (no copy engine, no stream
+ * synchronisation; the kernel may still be retiring when the call returns - later work on the
+ * same stream is ordered behind it as usual); otherwise they are copied and the stream is
+ * synchronised. */
 int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
                                    const int64_t *fan_out, int64_t num_nodes);
 int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
