@@ -1273,13 +1273,32 @@ extern "C" int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, 
   return 0;
 }
 
-extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
-                                 int num_layers, const int64_t *fan_out, int replace,
-                                 uint64_t rng_seed, void *const *out_frontier,
-                                 void *const *out_row, void *const *out_col,
-                                 const int64_t *cap_edges, const int64_t *cap_frontier,
-                                 int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
-                                 int64_t *counts_host, void *stream) {
+// Wait until the hop sizes of the batch enqueued with counts_host have arrived there.
+static int counts_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers, bool by_kernel,
+                       cudaStream_t st) {
+  if (by_kernel) {
+    volatile int64_t *flag = counts_host;
+    unsigned int spins = 0;
+    while (*flag == -1) {
+      if ((++spins & 0x3ffu) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;
+    }
+    if (*flag != -1) return 0;
+    // the stream drained (or failed) without the sizes arriving: take the copy path, which also
+    // reports a kernel fault
+  }
+  DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * num_layers,
+                              cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int sample_blocks_impl(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                              int num_layers, const int64_t *fan_out, int replace,
+                              uint64_t rng_seed, void *const *out_frontier,
+                              void *const *out_row, void *const *out_col,
+                              const int64_t *cap_edges, const int64_t *cap_frontier,
+                              int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
+                              int64_t *counts_host, void *stream, bool wait) {
   DGS_REQUIRE(g && fan_out && out_frontier && out_row && out_col && cap_edges && cap_frontier &&
                   counts_dev && ws,
               "dgs_sample_blocks: null argument");
@@ -1290,7 +1309,7 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
     DGS_CUDA_OK(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 2 * num_layers, st));
     if (counts_host) {
       memset(counts_host, 0, sizeof(int64_t) * 2 * num_layers);
-      DGS_CUDA_OK(cudaStreamSynchronize(st));
+      if (wait) DGS_CUDA_OK(cudaStreamSynchronize(st));
     }
     return 0;
   }
@@ -1323,7 +1342,7 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
       }
       host_dev = last_dev;
     }
-    if (host_dev) *(volatile int64_t *)counts_host = -1;   // sentinel: hop sizes are >= 0
+    if (host_dev || !wait) *(volatile int64_t *)counts_host = -1;   // sentinel: hop sizes are >= 0
   }
   int rc = 0;
   bool by_kernel = false;
@@ -1336,20 +1355,45 @@ extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_
   });
   if (rc) return rc;
   if (counts_host) {
+    // (not delivered by the kernel - unmapped memory or the multi-kernel path: the wait call
+    // finds the sentinel untouched once the stream has drained and copies the sizes itself)
+    if (!wait) return 0;
     // the one host round trip of the batch: hop sizes -> (pinned) host memory
-    if (by_kernel) {
-      volatile int64_t *flag = counts_host;
-      unsigned int spins = 0;
-      while (*flag == -1) {
-        if ((++spins & 0x3ffu) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;
-      }
-      if (*flag != -1) return 0;
-      // the stream drained (or failed) without the sizes arriving: take the copy path, which also
-      // reports a kernel fault
-    }
-    DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * num_layers,
-                                cudaMemcpyDeviceToHost, st));
-    DGS_CUDA_OK(cudaStreamSynchronize(st));
+    return counts_wait(counts_host, counts_dev, num_layers, by_kernel, st);
   }
   return 0;
+}
+
+extern "C" int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                                 int num_layers, const int64_t *fan_out, int replace,
+                                 uint64_t rng_seed, void *const *out_frontier,
+                                 void *const *out_row, void *const *out_col,
+                                 const int64_t *cap_edges, const int64_t *cap_frontier,
+                                 int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
+                                 int64_t *counts_host, void *stream) {
+  return sample_blocks_impl(g, seeds, num_seeds, num_layers, fan_out, replace, rng_seed, out_frontier,
+                            out_row, out_col, cap_edges, cap_frontier, counts_dev, ws, ws_bytes, epoch,
+                            counts_host, stream, true);
+}
+
+// Same, but returns right after the launch: the kernel will deliver the hop sizes to counts_host
+// (mapped pinned host memory, required) and dgs_sample_blocks_wait collects them - in between the
+// caller can enqueue the work that follows the sampling (dgs.classes.BatchLoader: extract + labels).
+extern "C" int dgs_sample_blocks_enqueue(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                                         int num_layers, const int64_t *fan_out, int replace,
+                                         uint64_t rng_seed, void *const *out_frontier,
+                                         void *const *out_row, void *const *out_col,
+                                         const int64_t *cap_edges, const int64_t *cap_frontier,
+                                         int64_t *counts_dev, void *ws, int64_t ws_bytes,
+                                         int64_t epoch, int64_t *counts_host, void *stream) {
+  DGS_REQUIRE(counts_host != nullptr, "dgs_sample_blocks_enqueue: counts_host is required");
+  return sample_blocks_impl(g, seeds, num_seeds, num_layers, fan_out, replace, rng_seed, out_frontier,
+                            out_row, out_col, cap_edges, cap_frontier, counts_dev, ws, ws_bytes, epoch,
+                            counts_host, stream, false);
+}
+
+extern "C" int dgs_sample_blocks_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers,
+                                      void *stream) {
+  DGS_REQUIRE(counts_host && counts_dev && num_layers >= 1, "dgs_sample_blocks_wait: bad argument");
+  return counts_wait(counts_host, counts_dev, num_layers, true, (cudaStream_t)stream);
 }

@@ -83,6 +83,10 @@ SIGNATURES = {
     "dgs_sample_blocks": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, C.c_int, c_i64p, C.c_int,
                                     C.c_uint64, c_vpp, c_vpp, c_vpp, c_i64p, c_i64p, c_vp, c_vp,
                                     c_i64, c_i64, c_vp, c_vp]),
+    "dgs_sample_blocks_enqueue": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, C.c_int, c_i64p, C.c_int,
+                                            C.c_uint64, c_vpp, c_vpp, c_vpp, c_i64p, c_i64p, c_vp, c_vp,
+                                            c_i64, c_i64, c_vp, c_vp]),
+    "dgs_sample_blocks_wait": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "dgs_relabel_table_capacity": (c_i64, [c_i64]),
     "dgs_relabel_table_bytes": (c_i64, [c_i64]),
     "dgs_relabel_ws_bytes": (c_i64, [c_i64]),

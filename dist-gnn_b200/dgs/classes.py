@@ -331,10 +331,12 @@ class _BlockPipeline:
             cur = frontier
         return out
 
-    def enqueue_only(self, seeds, fan_out, replace=False, rng_seed=1):
-        """Extension (bench.py's roofline leg): enqueue one batch WITHOUT the host round trip and
-        return the raw arena (worst-case sized, counts in its last 2 L int64).  Lets K batches be
-        issued back to back so the kernel's own duration can be timed with CUDA events."""
+    def enqueue_only(self, seeds, fan_out, replace=False, rng_seed=1, deliver_counts=False):
+        """Extension (bench.py's roofline leg, BatchLoader): enqueue one batch WITHOUT the host round
+        trip and return the raw arena (worst-case sized, counts in its last 2 L int64).  Lets K
+        batches be issued back to back so the kernel's own duration can be timed with CUDA events.
+        deliver_counts=True: the kernel also writes the hop sizes into the plan's pinned host
+        buffer; collect them with wait_counts()."""
         l = lib()
         fan_out = [int(k) for k in fan_out]
         L = len(fan_out)
@@ -349,13 +351,21 @@ class _BlockPipeline:
                 pl["a_fr"][li] = base + of * es
                 pl["a_row"][li] = base + orow * es
                 pl["a_col"][li] = base + ocol * es
-            check(l.dgs_sample_blocks(
+            fn = l.dgs_sample_blocks_enqueue if deliver_counts else l.dgs_sample_blocks
+            check(fn(
                 C.byref(self._graph), seeds.data_ptr(), S, L, pl["fo"], int(bool(replace)),
                 C.c_uint64(rng_seed), pl["a_fr"], pl["a_row"], pl["a_col"], pl["cap_edges"],
                 pl["cap_front"], base + pl["total"] * es, pl["ws"].data_ptr(), pl["ws_bytes"],
-                pl["epoch"], None, stream()), "sample_blocks")
+                pl["epoch"], pl["counts_ptr"] if deliver_counts else None, stream()), "sample_blocks")
             pl["epoch"] += 1
         return arena
+
+    def wait_counts(self, pl, arena):
+        """Block until the hop sizes of the batch enqueued with deliver_counts=True are in
+        pl["counts_np"] (polls the pinned buffer the kernel writes; no stream synchronisation)."""
+        with _on_device(self._device):
+            check(lib().dgs_sample_blocks_wait(pl["counts_ptr"], arena.data_ptr() + pl["total"] * pl["es"],
+                                               pl["L"], stream()), "sample_blocks_wait")
 
     def _sample_per_hop(self, seeds, fan_out, replace, rng_seed):
         """Host-synchronised hop loop (used for fan-out -1 = all neighbours, an extension)."""
@@ -698,7 +708,7 @@ class BatchLoader:
             pl = self._pipe._plan(seeds.numel(), fan_out)
             if pl["ws"] is None or seeds.numel() == 0:
                 raise RuntimeError("BatchLoader: batch too large for the fused path")
-            arena = self._pipe.enqueue_only(seeds, fan_out, replace, rng_seed)   # no host sync
+            arena = self._pipe.enqueue_only(seeds, fan_out, replace, rng_seed, deliver_counts=True)
             es, base = pl["es"], arena.data_ptr()
             counts_ptr = base + pl["total"] * es
             n_max = pl["ubs"][-1] + pl["nnz_ubs"][-1]
@@ -723,9 +733,9 @@ class BatchLoader:
             y = ops._CAPI_cuda_index_select(self._labels, seeds) if self._labels is not None else None
             if labels_out is not None and y is not None:
                 labels_out.copy_(y, non_blocking=True)
-            # the one host round trip: hop sizes -> pinned memory
-            pl["counts_host"].copy_(arena[pl["total"]:].view(torch.int64), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            # the one host round trip: the sampling kernel has written the hop sizes into pinned
+            # memory; the extract / label kernels enqueued above may still be running
+            self._pipe.wait_counts(pl, arena)
             counts = pl["counts_np"].tolist()
             sizes = []
             for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
@@ -740,11 +750,13 @@ class BatchLoader:
                      if self._fs is None else self._fs._CAPI_get_feature(parts[6 * (L - 1)], algo))
             else:
                 x = x[:nf]
-        blocks = []
-        cur = seeds
-        for li in range(L):
-            frontier = parts[6 * li]
-            blocks.append((cur, frontier, parts[6 * li + 2], parts[6 * li + 4]))
-            cur = frontier
+            blocks = []
+            cur = seeds
+            for li in range(L):
+                frontier = parts[6 * li]
+                blocks.append((cur, frontier, parts[6 * li + 2], parts[6 * li + 4]))
+                cur = frontier
+            if labels_out is not None and y is not None:
+                torch.cuda.current_stream().synchronize()    # labels_out is read by the host
         return blocks, x, y
 

@@ -224,6 +224,19 @@ int dgs_sample_blocks(const dgs_graph_t *g, const void *seeds, int64_t num_seeds
                       const int64_t *cap_edges, const int64_t *cap_frontier, int64_t *counts_dev,
                       void *ws, int64_t ws_bytes, int64_t epoch, int64_t *counts_host, void *stream);
 
+/* dgs_sample_blocks split in two (extension, used by dgs.classes.BatchLoader): _enqueue launches and
+ * returns at once - the kernel delivers the hop sizes to counts_host (required; mapped pinned host
+ * memory) - and _wait returns once they have arrived.  In between the caller enqueues whatever
+ * follows the sampling on the same stream (extract, label gather). */
+int dgs_sample_blocks_enqueue(const dgs_graph_t *g, const void *seeds, int64_t num_seeds,
+                              int num_layers, const int64_t *fan_out, int replace, uint64_t rng_seed,
+                              void *const *out_frontier, void *const *out_row, void *const *out_col,
+                              const int64_t *cap_edges, const int64_t *cap_frontier,
+                              int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t epoch,
+                              int64_t *counts_host, void *stream);
+int dgs_sample_blocks_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers,
+                           void *stream);
+
 /* ------------------------------------------------------------------ relabel
  * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):
  * unique = first-occurrence-order unique of the concatenation of the mapping parts, every id of
