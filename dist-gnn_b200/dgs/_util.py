@@ -1,9 +1,7 @@
 """Small host-side helpers shared by dgs.ops and dgs.classes."""
-import ctypes as C
 
 import torch
 
-from . import _lib
 
 ID_DTYPES = {torch.int32: 0, torch.int64: 1}
 # values the reference accepts (DGS_VALUE_TYPE_SWITCH, src/common/dgs_headers.h:60-74) plus the

@@ -6,7 +6,7 @@ import torch
 
 from . import _lib, ops
 from ._util import (ID_DTYPES, check_cpu, check_cuda, check_device_readable, contiguous, itype, ptr,
-                    stream, tensor_from_ptr, zero_ws)
+                    stream, tensor_from_ptr)
 
 lib = _lib.lib
 check = _lib.check

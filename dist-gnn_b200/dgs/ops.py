@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 from ._util import (MAX_TWO_PASS_ELEMS, check_cpu, check_cuda, check_device_readable, contiguous,
-                    device_of_current, itype, ptr, stream, zero_ws)
+                    itype, ptr, stream, zero_ws)
 
 lib = _lib.lib
 check = _lib.check
