@@ -1,10 +1,7 @@
 """CPU: host-side logic - seed iterator, synthetic generators, shard partitioning, and the N > 1
 bootstrap / reduction logic on a world_size-2 gloo group (no GPU)."""
-import os
 import socket
-import sys
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -29,6 +26,38 @@ def test_seed_generator_matches_reference_semantics():
     # second epoch reshuffles
     again = torch.cat(list(g))
     assert sorted(again.tolist()) == list(range(10))
+
+
+def test_seed_generator_edges():
+    data = torch.arange(12)
+    g = SeedGenerator(data, 4)
+    assert len(g) == 3 and g.is_finished()            # usable before the first epoch starts
+    with pytest.raises(StopIteration):
+        next(g)
+    it = iter(g)
+    first = next(it)
+    assert first.data_ptr() == data.data_ptr() and not g.is_finished()    # a view, not a copy
+    assert [next(it).tolist(), next(it).tolist()] == [[4, 5, 6, 7], [8, 9, 10, 11]]
+    assert g.step == g.last_step == 3 and g.is_finished()
+    assert [b.tolist() for b in it][0] == [0, 1, 2, 3]      # iter() starts a new epoch, as in the reference
+    assert len(SeedGenerator(data, 5, drop_last=True)) == 2 and len(SeedGenerator(data, 5)) == 3
+    assert len(SeedGenerator(data[:0], 5)) == 0 and list(SeedGenerator(data[:0], 5)) == []
+    assert [b.tolist() for b in SeedGenerator(data[:1], 5, shuffle=True)] == [[0]]
+    with pytest.raises(ValueError):
+        SeedGenerator(data, 0)
+
+
+def test_build_blocks_orders_blocks_input_side_first():
+    """Host logic of DistGNN.dataloading.build_blocks (the CSC kernel itself is a GPU test)."""
+    from DistGNN.dataloading import NID, build_blocks
+    hop0 = (torch.tensor([7, 9]), torch.tensor([7, 9, 3]), torch.tensor([0, 1]), torch.tensor([2, 0]))
+    hop1 = (hop0[1], torch.tensor([7, 9, 3, 5]), torch.tensor([0, 2, 2]), torch.tensor([1, 3, 0]))
+    blocks = build_blocks([hop0, hop1], capi=object())
+    assert [b.num_dst_nodes() for b in blocks] == [3, 2] and [b.num_src_nodes() for b in blocks] == [4, 3]
+    assert [b.num_edges() for b in blocks] == [3, 2]
+    assert torch.equal(blocks[0].dstdata[NID], blocks[1].srcdata[NID])
+    src, dst = blocks[1].edges()
+    assert src.tolist() == [2, 0] and dst.tolist() == [0, 1]
 
 
 def test_synth_is_deterministic_and_shaped():
