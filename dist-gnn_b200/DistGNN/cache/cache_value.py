@@ -46,7 +46,7 @@ def get_node_heat(indptr, indices, node_ids, fan_outs, probs=None, mode="uva", c
     sampling_heat = torch.zeros(num_nodes).cuda()
     seeds_heat = torch.zeros(num_nodes).cuda()
     seeds_heat[node_ids] = 1
-    seeds = node_ids.cuda()
+    seeds = node_ids.cuda().to(indices.dtype)   # the heat kernel reads seeds with indices' id type
     frontier_heat = torch.zeros(num_nodes).cuda()
     for num_picks in reversed(list(fan_outs)):
         if probs is None:

@@ -20,6 +20,7 @@ class Block:
         self.srcdata = {NID: frontier}
         self.dstdata = {NID: seeds}
         self._indptr = None
+        self._src = self._eid = None
 
     def num_src_nodes(self):
         return self.srcdata[NID].numel()
@@ -37,9 +38,27 @@ class Block:
     def csc(self):
         """(indptr over dst nodes, src ids, edge ids) - adj_tensors('csc') of the DGL block."""
         if self._indptr is None:
-            self._indptr = self._capi.ops.coo_rows_to_indptr(self._row, self.num_dst_nodes())
-        return self._indptr, self._col, torch.arange(self.num_edges(), dtype=self._col.dtype,
-                                                     device=self._col.device)
+            try:
+                # the sampler emits edges grouped by destination when the hop's seeds are distinct
+                self._indptr = self._capi.ops.coo_rows_to_indptr(self._row, self.num_dst_nodes(),
+                                                                 check_sorted=True)
+                self._src = self._col
+                self._eid = torch.arange(self.num_edges(), dtype=self._col.dtype,
+                                         device=self._col.device)
+            except RuntimeError as e:
+                if "ascending" not in str(e):
+                    raise
+                # duplicate seeds in the first hop: rows are first-occurrence ids, not ascending ->
+                # stable sort by destination (what dgl.create_block's COO->CSC conversion does)
+                order = torch.argsort(self._row, stable=True)
+                deg = torch.bincount(self._row.long(), minlength=self.num_dst_nodes())
+                indptr = torch.zeros(self.num_dst_nodes() + 1, dtype=self._row.dtype,
+                                     device=self._row.device)
+                indptr[1:] = torch.cumsum(deg, 0)
+                self._indptr = indptr
+                self._src = self._col[order]
+                self._eid = order.to(self._col.dtype)
+        return self._indptr, self._src, self._eid
 
     def in_degrees(self):
         indptr = self.csc()[0]

@@ -1108,7 +1108,7 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
       *host_counts_used = host_counts != nullptr;
       void *params[] = {&src_copy, &ws_copy, &a};
       DGS_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kBkThreads), params, smem_max, st));
-      dgsb::g_launches += 1;
+      dgsb::g_launches.fetch_add(1, std::memory_order_relaxed);
       if (trace) {
         unsigned long long h[1 + 8 * 16];
         cudaStreamSynchronize(st);

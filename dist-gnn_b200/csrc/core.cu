@@ -1,6 +1,7 @@
 // core.cu - errors, launch counter, random engine, pin memory.
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 #include <random>
 
@@ -9,7 +10,7 @@
 namespace dgsb {
 
 static thread_local char g_err[1024] = "";
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -48,7 +49,7 @@ extern "C" {
 
 int dgs_abi_version(void) { return DGS_B200_ABI_VERSION; }
 const char *dgs_last_error(void) { return dgsb::g_err; }
-int64_t dgs_launch_count(void) { return dgsb::g_launches; }
+int64_t dgs_launch_count(void) { return dgsb::g_launches.load(std::memory_order_relaxed); }
 int dgs_sm_count(void) { return dgsb::sm_count(); }
 
 uint64_t dgs_randn_uint64(void) {

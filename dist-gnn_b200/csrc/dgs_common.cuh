@@ -5,13 +5,15 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/dgs_b200.h"
 
 namespace dgsb {
 
 // ---------------------------------------------------------------- errors / bookkeeping
 void set_error(const char *fmt, ...);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 int sm_count();
 
 #define DGS_CUDA_OK(call)                                                              \
@@ -34,7 +36,7 @@ int sm_count();
 
 #define DGS_LAUNCH_CHECK()                  \
   do {                                      \
-    dgsb::g_launches += 1;                  \
+    dgsb::g_launches.fetch_add(1, std::memory_order_relaxed); \
     DGS_CUDA_OK(cudaGetLastError());        \
   } while (0)
 

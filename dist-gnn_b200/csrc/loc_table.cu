@@ -14,21 +14,41 @@
 
 namespace dgsb {
 
+// set by loc_insert_kernel when a key found no slot (more distinct ids than capacity - 1) or was
+// negative; read back (and cleared) by dgs_loc_table_build after the inserts
+__device__ int g_loc_build_error;
+
 template <typename IdT>
 __global__ void loc_insert_kernel(LocSlot *table, uint64_t cap_mask, const IdT *__restrict__ nids,
                                   int64_t n, long long dev_bits) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     long long key = (long long)nids[i];
+    if (key < 0) {   // -1 is the empty marker
+      g_loc_build_error = 2;
+      continue;
+    }
     uint64_t pos = mix64((uint64_t)key) & cap_mask;
-    while (true) {
+    // an id cached on several devices occupies ONE slot (the reference's Update() overwrites the
+    // entry, hashmap.h:18-32), so only the number of DISTINCT ids is bounded by the capacity; the
+    // probe sequence is cut after one full cycle instead of trusting a host-side total
+    uint64_t probes = 0;
+    bool placed = false;
+    while (probes <= cap_mask) {
       unsigned long long prev =
           atomicCAS((unsigned long long *)&table[pos].key, (unsigned long long)kEmptyKey,
                     (unsigned long long)key);
-      if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)key) break;
+      if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)key) {
+        placed = true;
+        break;
+      }
       pos = (pos + 1) & cap_mask;
+      ++probes;
     }
-    atomicMax(&table[pos].val, dev_bits | (long long)i);
+    if (placed)
+      atomicMax(&table[pos].val, dev_bits | (long long)i);
+    else
+      g_loc_build_error = 1;
   }
 }
 
@@ -77,14 +97,18 @@ extern "C" int dgs_loc_table_build(void *table, int64_t capacity, int itype, int
               "dgs_loc_table_build: capacity %lld is not a power of two", (long long)capacity);
   DGS_REQUIRE(world >= 1 && world <= DGS_MAX_DEVICES && rank >= 0 && rank < world,
               "dgs_loc_table_build: bad world/rank %d/%d", world, rank);
-  int64_t total = 0;
+  // ids cached on several ranks share a slot, so sum(counts) may exceed the capacity (every GPU
+  // caching the same hubs - the "selfish" policy - gives sum = world * n_unique); each single list
+  // holds distinct ids and must fit on its own, the union is checked by the insert kernel
   for (int d = 0; d < world; ++d) {
     DGS_REQUIRE(counts[d] >= 0 && counts[d] <= kIdxMask, "dgs_loc_table_build: bad count");
-    total += counts[d];
+    DGS_REQUIRE(counts[d] < capacity, "dgs_loc_table_build: the %lld ids of device %d do not fit "
+                "capacity %lld", (long long)counts[d], d, (long long)capacity);
   }
-  DGS_REQUIRE(total < capacity, "dgs_loc_table_build: %lld ids do not fit capacity %lld",
-              (long long)total, (long long)capacity);
   cudaStream_t st = (cudaStream_t)stream;
+  int zero = 0;
+  DGS_CUDA_OK(cudaMemcpyToSymbolAsync(g_loc_build_error, &zero, sizeof(int), 0,
+                                      cudaMemcpyHostToDevice, st));
   DGS_CUDA_OK(cudaMemsetAsync(table, 0xFF, (size_t)capacity * sizeof(LocSlot), st));
   for (int d = 0; d < world; ++d) {
     if (counts[d] == 0) continue;
@@ -98,6 +122,14 @@ extern "C" int dgs_loc_table_build(void *table, int64_t capacity, int itype, int
     });
     DGS_LAUNCH_CHECK();
   }
+  // build time only: one round trip for the overflow flag
+  int err = 0;
+  DGS_CUDA_OK(cudaMemcpyFromSymbolAsync(&err, g_loc_build_error, sizeof(int), 0,
+                                        cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));
+  DGS_REQUIRE(err != 1, "dgs_loc_table_build: more distinct ids than the capacity %lld holds",
+              (long long)capacity);
+  DGS_REQUIRE(err == 0, "dgs_loc_table_build: negative node id in a cache list");
   return 0;
 }
 

@@ -12,11 +12,14 @@
 // reference cudaHostRegister()s stack memory and hands it to NCCL, tensor_p2p_cache.cc:54-63).
 #include <cuda.h>
 #include <dlfcn.h>
+#include <errno.h>
+#include <poll.h>
 #include <nccl.h>
 #include <sys/socket.h>
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -199,32 +202,52 @@ static int recv_fd(int sock) {
   return fd;
 }
 
-// every rank serves its own fd to the world-1 peers and fetches theirs; returns 0 on success
+// every rank serves its own fd to the world-1 peers and fetches theirs; returns 0 on success.
+// Collective: EVERY rank runs both barriers whatever happened locally, so a rank whose socket set-up
+// or a peer connection failed cannot leave the others blocked: the accept loop polls with a
+// timeout and is told to stop once every rank has finished its client side (second barrier) - by
+// then no peer can still be waiting for this rank's fd.
 static int exchange_fds(int my_fd, int world, int rank, int64_t serial, int *peer_fds) {
   sockaddr_un addr;
   socklen_t alen;
   sock_name(&addr, &alen, serial, rank);
   int srv = socket(AF_UNIX, SOCK_STREAM, 0);
+  int err = 0;
   if (srv < 0 || bind(srv, (sockaddr *)&addr, alen) != 0 || listen(srv, world) != 0) {
     if (srv >= 0) close(srv);
-    return -1;
+    srv = -1;
+    err = 1;
   }
+  std::atomic<int> stop{0};
   int srv_err = 0;
-  std::thread server([&]() {
-    for (int i = 0; i < world - 1; ++i) {
-      int c = accept(srv, nullptr, nullptr);
-      if (c < 0 || send_fd(c, my_fd) != 0) srv_err = 1;
-      if (c >= 0) close(c);
-    }
-  });
-  int err = 0;
-  if (dgs_nccl_barrier()) err = 1;  // every rank is listening
-  for (int p = 0; p < world && !err; ++p) {
+  std::thread server;
+  if (srv >= 0) {
+    server = std::thread([&]() {
+      int served = 0;
+      while (served < world - 1 && !stop.load(std::memory_order_acquire)) {
+        pollfd pfd{srv, POLLIN, 0};
+        const int pr = poll(&pfd, 1, 100 /* ms */);
+        if (pr < 0 && errno != EINTR) {
+          srv_err = 1;
+          break;
+        }
+        if (pr <= 0 || !(pfd.revents & POLLIN)) continue;
+        int c = accept(srv, nullptr, nullptr);
+        if (c < 0 || send_fd(c, my_fd) != 0) srv_err = 1;
+        if (c >= 0) close(c);
+        ++served;
+      }
+    });
+  }
+  if (dgs_nccl_barrier()) err = 1;  // every rank that could is listening
+  for (int p = 0; p < world; ++p) {
     if (p == rank) continue;
     sockaddr_un pa;
     socklen_t pl;
     sock_name(&pa, &pl, serial, p);
     int c = socket(AF_UNIX, SOCK_STREAM, 0);
+    timeval tv{30, 0};  // a peer that listens but never serves must not block us for ever
+    if (c >= 0) setsockopt(c, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
     if (c < 0 || connect(c, (sockaddr *)&pa, pl) != 0) {
       err = 1;
     } else {
@@ -233,13 +256,10 @@ static int exchange_fds(int my_fd, int world, int rank, int64_t serial, int *pee
     }
     if (c >= 0) close(c);
   }
-  if (err) {
-    // unblock our own server thread: connect to ourselves for the accepts that will never come
-    // (peers that failed); best effort - a failed exchange is fatal for the caller anyway
-    shutdown(srv, SHUT_RDWR);
-  }
-  server.join();
-  close(srv);
+  if (dgs_nccl_barrier()) err = 1;  // every rank has finished fetching: nobody waits for us any more
+  stop.store(1, std::memory_order_release);
+  if (server.joinable()) server.join();
+  if (srv >= 0) close(srv);
   return (err || srv_err) ? -1 : 0;
 }
 
@@ -266,8 +286,12 @@ static int vmm_map(dgs_p2p_server *s, int slot, int dev, CUmemGenericAllocationH
   return 0;
 }
 
+static void vmm_destroy(dgs_p2p_server *s);
+
 // returns 0 on success, 1 when the VMM path is unavailable (caller falls back to legacy IPC),
-// >= 2 on a hard error (set_error called)
+// >= 2 on a hard error (set_error called).  After the availability agreement every rank walks
+// through the SAME sequence of collectives whatever fails locally; failures are accumulated and
+// agreed on at the end, then everything mapped so far is released on every rank.
 static int vmm_create(dgs_p2p_server *s, const void *dev_src, int64_t nbytes) {
   if (getenv("DGS_P2P_LEGACY_IPC")) return 1;  // (set it on every rank or on none)
   int dev = 0;
@@ -291,7 +315,11 @@ static int vmm_create(dgs_p2p_server *s, const void *dev_src, int64_t nbytes) {
   }
   // all ranks must take the same path: agree on availability
   std::vector<int64_t> flags(s->world);
-  if (dgs_nccl_allgather_i64(have, flags.data())) return 2;
+  if (dgs_nccl_allgather_i64(have, flags.data())) {
+    if (fd >= 0) close(fd);
+    if (h) g_drv.MemRelease(h);
+    return 2;
+  }
   bool all = true;
   for (int i = 0; i < s->world; ++i) all = all && flags[i] == 1;
   if (!all) {
@@ -300,40 +328,58 @@ static int vmm_create(dgs_p2p_server *s, const void *dev_src, int64_t nbytes) {
     return 1;
   }
   s->vmm = 1;
+  int fail = 0;
+  char why[256] = "";
   if (vmm_map(s, s->rank, dev, h, size, gran) != 0) {
-    set_error("dgs_p2p_server_create: cuMemMap of the local shard (%zu bytes) failed", size);
-    return 2;
+    snprintf(why, sizeof(why), "cuMemMap of the local shard (%zu bytes) failed", size);
+    g_drv.MemRelease(h);   // never mapped: vmm_destroy will not see it
+    fail = 1;
   }
-  if (dev_src) {
+  if (!fail && dev_src) {
     cudaError_t e = cudaMemcpy(s->ptrs[s->rank], dev_src, (size_t)nbytes, cudaMemcpyDefault);
     if (e != cudaSuccess) {
-      set_error("dgs_p2p_server_create: copy failed: %s", cudaGetErrorString(e));
-      return 2;
+      snprintf(why, sizeof(why), "copy into the shard failed: %s", cudaGetErrorString(e));
+      fail = 1;
     }
   }
   std::vector<int64_t> sizes(s->world), msizes(s->world);
-  if (dgs_nccl_allgather_i64(nbytes, sizes.data())) return 2;
-  if (dgs_nccl_allgather_i64((int64_t)size, msizes.data())) return 2;
+  if (dgs_nccl_allgather_i64(nbytes, sizes.data())) fail = 1;
+  if (dgs_nccl_allgather_i64((int64_t)size, msizes.data())) fail = 1;
   std::vector<int> fds(s->world, -1);
   const int64_t serial = g_ctx.serial++;
   if (exchange_fds(fd, s->world, s->rank, serial, fds.data()) != 0) {
-    set_error("dgs_p2p_server_create: fd exchange over unix sockets failed");
-    close(fd);
-    return 2;
+    if (!fail) snprintf(why, sizeof(why), "fd exchange over unix sockets failed");
+    fail = 1;
   }
   close(fd);
   for (int i = 0; i < s->world; ++i) {
     s->nbytes[i] = sizes[i];
-    if (i == s->rank) continue;
-    CUmemGenericAllocationHandle ph = 0;
-    if (g_drv.MemImportFromShareableHandle(&ph, (void *)(uintptr_t)fds[i], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS ||
-        vmm_map(s, i, dev, ph, (size_t)msizes[i], gran) != 0) {
-      set_error("dgs_p2p_server_create: importing / mapping the shard of rank %d failed", i);
-      return 2;
+    if (i == s->rank || fds[i] < 0) continue;
+    if (!fail) {
+      CUmemGenericAllocationHandle ph = 0;
+      if (g_drv.MemImportFromShareableHandle(&ph, (void *)(uintptr_t)fds[i], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) {
+        snprintf(why, sizeof(why), "importing the shard of rank %d failed", i);
+        fail = 1;
+      } else if (vmm_map(s, i, dev, ph, (size_t)msizes[i], gran) != 0) {
+        snprintf(why, sizeof(why), "mapping the shard of rank %d failed", i);
+        g_drv.MemRelease(ph);
+        fail = 1;
+      }
     }
     close(fds[i]);
   }
-  if (dgs_nccl_barrier()) return 2;
+  // agree on the outcome (also the barrier after which every shard may be read)
+  bool any_fail = fail != 0;
+  if (dgs_nccl_allgather_i64(fail, flags.data()))
+    any_fail = true;
+  else
+    for (int i = 0; i < s->world; ++i) any_fail = any_fail || flags[i] != 0;
+  if (any_fail) {
+    vmm_destroy(s);   // unmaps / releases whatever was mapped, here and (same decision) on every rank
+    memset(s->ptrs, 0, sizeof(s->ptrs));
+    set_error("dgs_p2p_server_create: %s", why[0] ? why : "shard set-up failed on another rank");
+    return 2;
+  }
   return 0;
 }
 
@@ -493,18 +539,36 @@ int dgs_p2p_server_create(const void *dev_src, int64_t nbytes, dgs_p2p_server_t 
       cudaIpcMemHandle_t h;  // 64 bytes
     } mine;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle is 64 bytes");
-    DGS_CUDA_OK(cudaIpcGetMemHandle(&mine.h, local));
+    // errors below release everything this call opened / allocated before returning
+    auto fail = [&](int rc) {
+      for (int i = 0; i < s->world; ++i)
+        if (i != s->rank && s->ptrs[i]) cudaIpcCloseMemHandle(s->ptrs[i]);
+      cudaFree(local);
+      delete s;
+      return rc;
+    };
+    cudaError_t ce = cudaIpcGetMemHandle(&mine.h, local);
+    if (ce != cudaSuccess) {
+      set_error("dgs_p2p_server_create: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(ce));
+      return fail(100 + (int)ce);
+    }
     std::vector<Msg> all(s->world);
-    if (allgather_small(&mine, sizeof(mine), all.data())) return 1;
+    if (allgather_small(&mine, sizeof(mine), all.data())) return fail(1);
     std::vector<int64_t> sizes(s->world);
-    if (dgs_nccl_allgather_i64(nbytes, sizes.data())) return 1;
+    if (dgs_nccl_allgather_i64(nbytes, sizes.data())) return fail(1);
     for (int i = 0; i < s->world; ++i) {
       s->nbytes[i] = sizes[i];
       if (i == s->rank) continue;
-      DGS_CUDA_OK(cudaIpcOpenMemHandle(&s->ptrs[i], all[i].h, cudaIpcMemLazyEnablePeerAccess));
+      ce = cudaIpcOpenMemHandle(&s->ptrs[i], all[i].h, cudaIpcMemLazyEnablePeerAccess);
+      if (ce != cudaSuccess) {
+        s->ptrs[i] = nullptr;
+        set_error("dgs_p2p_server_create: cudaIpcOpenMemHandle(rank %d) failed: %s", i,
+                  cudaGetErrorString(ce));
+        return fail(100 + (int)ce);
+      }
     }
     s->ipc_opened = 1;
-    if (dgs_nccl_barrier()) return 1;
+    if (dgs_nccl_barrier()) return fail(1);
   }
   *out = s;
   return 0;

@@ -242,6 +242,17 @@ static int launch_sample(const GraphSrc &g, const IdT *seeds, int64_t num_seeds,
   return 0;
 }
 
+// Test hook: the A-Res key of every edge t of one row, exactly as every biased selection path
+// computes it (ares_key over Philox word t of (rng_key, item)).  The k largest keys (ties: smaller
+// position first) ARE the weighted sample without replacement, so a test can check any selection
+// path exactly with a top-k over this array.
+__global__ void ares_keys_kernel(const float *__restrict__ w, int64_t deg, uint64_t rng_key,
+                                 uint64_t item, float *__restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < deg;
+       t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = ares_key(philox_u32(rng_key, item, (uint32_t)t), w[t]);
+}
+
 int build_graph_src(const dgs_graph_t *g, GraphSrc *out) {
   memset(out, 0, sizeof(*out));
   out->indptr = g->indptr;
@@ -273,6 +284,17 @@ int build_graph_src(const dgs_graph_t *g, GraphSrc *out) {
 
 using namespace dgsb;
 
+extern "C" int dgs_debug_ares_keys(const float *weights, int64_t deg, uint64_t rng_key, uint64_t item,
+                                   float *keys_out, void *stream) {
+  DGS_REQUIRE(deg >= 0 && deg < (1ll << 32), "dgs_debug_ares_keys: bad degree");
+  if (deg == 0) return 0;
+  DGS_REQUIRE(weights && keys_out, "dgs_debug_ares_keys: null pointer");
+  ares_keys_kernel<<<grid_for(deg, 256, 8), 256, 0, (cudaStream_t)stream>>>(weights, deg, rng_key, item,
+                                                                          keys_out);
+  DGS_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int64_t dgs_sample_ws_bytes(int64_t max_seeds) {
   if (max_seeds < 1) max_seeds = 1;
   return ws_layout(max_seeds, nullptr, nullptr);
@@ -286,7 +308,6 @@ extern "C" int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int
   DGS_REQUIRE(g != nullptr, "dgs_sample_neighbors: null graph");
   DGS_REQUIRE(num_seeds >= 0, "dgs_sample_neighbors: negative seed count");
   DGS_REQUIRE(out_nnz_dev && ws, "dgs_sample_neighbors: null nnz / workspace");
-  DGS_REQUIRE(num_picks != 0 || true, "unreachable");
   DGS_REQUIRE(!(replace && num_picks < 0),
               "dgs_sample_neighbors: num_picks=-1 (all neighbours) cannot be combined with replace");
   cudaStream_t st = (cudaStream_t)stream;

@@ -301,8 +301,7 @@ __device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
       // fill the reservoir with the first k items
       for (int t = lane; t < k; t += 32) {
         const float w = wrow[t];
-        const float u = u32_to_unit(philox_u32(rng_key, item, (uint32_t)t));
-        w_key[t] = w > 0.f ? __log2f(u) / w : -INFINITY;
+        w_key[t] = ares_key(philox_u32(rng_key, item, (uint32_t)t), w);
         w_idx[t] = t;
       }
       __syncwarp();
@@ -348,7 +347,7 @@ __device__ __forceinline__ void warp_select(const IdT *__restrict__ row,
             const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
   #pragma unroll
             for (int c = 0; c < 4; ++c)
-              if (w4[q][c] > 0.f) key4[c] = __log2f(u32_to_unit(rr[c])) / w4[q][c];
+              if (tb + c >= k && tb + c < deg) key4[c] = ares_key(rr[c], w4[q][c]);
           }
   #pragma unroll
           for (int c = 0; c < 4; ++c) {

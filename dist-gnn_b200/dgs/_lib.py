@@ -78,6 +78,7 @@ SIGNATURES = {
     "dgs_sample_ws_bytes": (c_i64, [c_i64]),
     "dgs_sample_neighbors": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, c_vp, c_i64, C.c_int,
                                        C.c_uint64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dgs_debug_ares_keys": (C.c_int, [c_vp, c_i64, C.c_uint64, C.c_uint64, c_vp, c_vp]),
     "dgs_sample_blocks_ws_bytes": (c_i64, [C.c_int, c_i64, C.c_int, c_i64p, c_i64]),
     "dgs_sample_blocks_ws_init": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, C.c_int, c_i64p, c_i64, c_vp]),
     "dgs_sample_blocks": (C.c_int, [C.POINTER(Graph), c_vp, c_i64, C.c_int, c_i64p, C.c_int,

@@ -38,8 +38,9 @@ def _barrier():
 class TensorP2PServer:
     """cache::TensorP2PServer (src/cache/tensor_p2p_cache.h:43-73, tensor_p2p_cache.cc:11-132).
 
-    Copies a CUDA tensor into a raw cudaMalloc shard and maps every peer's shard through CUDA IPC.
-    Construction is collective over the NCCL context.  Unlike the reference the destructor does NOT
+    Copies a CUDA tensor into a VMM shard (cuMemCreate; the fd is passed to the peers of the box and
+    cuMemMap'ped there - legacy cudaMalloc + CUDA IPC only as a fallback) so that every rank holds a
+    pointer table of all shards.  Construction is collective over the NCCL context.  Unlike the reference the destructor does NOT
     run a collective (tensor_p2p_cache.cc:115 barriers inside ~TensorP2PServer, which deadlocks under
     Python GC ordering); call ``close()`` on all ranks for a synchronised teardown."""
 
@@ -205,6 +206,19 @@ def _unpack_loc_table(table, cap, dtype):
     check(lib().dgs_loc_table_unpack(ptr(table), cap, itype(key), ptr(key), ptr(idx), ptr(dev),
                                      stream()), "location table unpack")
     return key, idx, dev
+
+
+def _check_ids_in_range(indices, num_nodes, what="indices"):
+    """The fused batch path addresses its relabel tables directly by node id (8 bytes per node), so
+    a neighbour id outside [0, num_nodes) would be an out-of-bounds atomic: validate once at build
+    time (one reduction over the edge array; the reference never checks)."""
+    if indices is None or indices.numel() == 0:
+        return
+    lo, hi = torch.aminmax(indices)
+    lo, hi = int(lo), int(hi)
+    if lo < 0 or hi >= num_nodes:
+        raise RuntimeError(f"{what} holds node id {lo if lo < 0 else hi} outside [0, {num_nodes}) "
+                           f"(num_nodes = len(indptr) - 1)")
 
 
 def _host_source(t, name, all_cached):
@@ -393,6 +407,7 @@ class CSRSampler:
         self._keep = (indptr, indices, probs)
         if device is None:
             device = indices.device if indices.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        _check_ids_in_range(indices, indptr.numel() - 1)
         g = ops._make_graph(indptr, indices, probs if probs is not None and probs.numel() else None)
         g.num_nodes = indptr.numel() - 1    # known node count: direct-addressed relabel tables
         self._pipe = _BlockPipeline(g, device, indices.dtype)
@@ -435,6 +450,8 @@ class P2PCacheSampler:
                 nids = nids.to(indices.dtype)
             sub_indptr = ops._Test_ExtractIndptr(nids, indptr)
             sub_indices = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, indices)
+            # (un-cached rows are read from the caller's pinned arrays: check those as a whole)
+            _check_ids_in_range(indices, num_nodes)
             sub_probs = ops._Test_ExtractEdgeData(nids, indptr, sub_indptr, probs) if self.bias_ else None
             self._adopt_shards(sub_indptr, sub_indices, sub_probs, nids, num_nodes)
 
@@ -505,6 +522,8 @@ class P2PCacheSampler:
         self.bias_ = sub_probs is not None and sub_probs.numel() > 0
         self.cpu_indptr_, self.cpu_indices_ = cpu_indptr, cpu_indices
         self.cpu_probs_ = cpu_probs if self.bias_ else None
+        _check_ids_in_range(sub_indices, int(num_nodes), "sub_indices")
+        _check_ids_in_range(cpu_indices, int(num_nodes), "cpu_indices")
         self._adopt_shards(sub_indptr.contiguous(), sub_indices.contiguous(),
                            sub_probs.contiguous() if self.bias_ else None,
                            cache_nids.contiguous().to(sub_indices.dtype), int(num_nodes))

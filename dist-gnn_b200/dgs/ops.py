@@ -229,6 +229,20 @@ def _CAPI_cuda_sample_neighbors_bias(seeds, indptr, indices, probs, num_picks, r
     return _sample_one_hop(g, seeds, num_picks, replace, rng_seed)
 
 
+def _Test_AresKeys(weights, rng_key, item):
+    """Test hook: A-Res keys of one row for (rng_key, item); the k largest (ties: smaller position
+    first) are the weighted sample without replacement every biased path must return."""
+    check_cuda(weights, "weights")
+    weights = weights.contiguous()
+    if weights.dtype != torch.float32:
+        raise RuntimeError("weights must be float32")
+    out = torch.empty_like(weights)
+    check(lib().dgs_debug_ares_keys(ptr(weights), weights.numel(),
+                                    C.c_uint64(int(rng_key) & 0xFFFFFFFFFFFFFFFF),
+                                    C.c_uint64(int(item)), ptr(out), stream()), "_Test_AresKeys")
+    return out
+
+
 # ------------------------------------------------------------------ relabel
 def _relabel(mapping, to_relabel, table=None, capacity=None):
     l = lib()
@@ -283,6 +297,10 @@ def _heat(seeds, indptr, indices, probs, seeds_heat, num_picks, indptr_diff):
     check_device_readable(indices, "indices")
     if seeds_heat.dtype != torch.float32:
         raise RuntimeError("seeds_heat must be float32")
+    if seeds.dtype != indices.dtype:
+        # the kernel reads both through one id type (the reference throws on data_ptr<IdType>)
+        raise RuntimeError(f"seeds ({seeds.dtype}) and indices ({indices.dtype}) must share an id type")
+    seeds = seeds.contiguous()
     out = torch.zeros_like(seeds_heat)
     check(lib().dgs_frontier_heat(itype(indices, "indices"), itype(indptr, "indptr"), ptr(seeds),
                                   seeds.numel(), ptr(indptr), ptr(indices),
@@ -307,10 +325,13 @@ def _CAPI_compute_frontier_heat_with_bias(seeds, indptr, indices, probs, seeds_h
 
 # ------------------------------------------------------------------ block construction (extension)
 def coo_rows_to_indptr(coo_row, num_rows, check_sorted=False):
-    """CSC row pointer (num_rows + 1 entries, id dtype) of a sampled hop whose `coo_row` is ascending
-    - which every sampling op here guarantees.  Replaces what dgl.create_block derives in the caller
-    (example/graphsage/node_classification.py:18-28).  check_sorted=True verifies the precondition
-    (one host sync) and raises if it does not hold."""
+    """CSC row pointer (num_rows + 1 entries, id dtype) of a sampled hop whose `coo_row` is ascending.
+    Every sampling entry point emits it so WHEN THE HOP'S SEEDS ARE DISTINCT (always true from the
+    second hop on - the seeds are a frontier); a duplicate seed in hop 0 is relabelled to the id of
+    its first occurrence, which breaks the order.  Replaces what dgl.create_block derives in the
+    caller (example/graphsage/node_classification.py:18-28).  check_sorted=True verifies the
+    precondition (one host sync) and raises if it does not hold; without it the result for
+    unsorted rows is undefined (DistGNN.dataloading.Block checks and falls back to a sort)."""
     check_cuda(coo_row, "coo_row")
     coo_row = coo_row.contiguous()
     indptr = torch.empty(int(num_rows) + 1, dtype=coo_row.dtype, device=coo_row.device)

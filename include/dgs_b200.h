@@ -76,8 +76,11 @@ int dgs_nccl_allgatherv(const void *send_dev, int64_t send_bytes, void *const *r
 /* ------------------------------------------------------------------ tensor p2p server
  * replaces cache::TensorP2PServer + tensor_p2p_server_wrapper::At
  * (src/cache/tensor_p2p_cache.h:11-73, tensor_p2p_cache.cc:11-132).
- * A shard is one raw cudaMalloc copy of the caller's device buffer; every rank of the NCCL
- * context gets a void*[world] table of CUDA-IPC mapped peer shards. */
+ * A shard is a copy of the caller's device buffer in a cuMemCreate (VMM) allocation whose POSIX fd
+ * is handed to the other ranks of the box over unix sockets (SCM_RIGHTS) and cuMemMap'ped there;
+ * every rank of the NCCL context gets a void*[world] table of mapped peer shards.  (Fallback when
+ * VMM is unavailable on some rank, or DGS_P2P_LEGACY_IPC=1: raw cudaMalloc + CUDA-IPC handles, the
+ * reference's mechanism - measured 8x slower for random row reads on B200.) */
 typedef struct dgs_p2p_server dgs_p2p_server_t;
 /* collective over the NCCL context (world 1: purely local).  dev_src == NULL allocates the shard
  * without copying (the caller fills dgs_p2p_server_ptr(s, rank) in place). */
@@ -193,6 +196,14 @@ int dgs_sample_neighbors(const dgs_graph_t *g, const void *seeds, int64_t num_se
                          uint64_t rng_seed, void *out_row, void *out_col, int64_t out_capacity,
                          int64_t *out_nnz_dev, void *ws, void *stream);
 
+/* Test hook (like the reference's _Test_* entries, src/pybind.cc:72-77): keys_out[t] = the A-Res
+ * key log2(u_t) / w_t of edge t of a row of `deg` weights for (rng_key, item) - the k largest keys
+ * (ties: smaller t first) are exactly what biased sampling without replacement returns for seed
+ * index `item` under launch key rng_key (dgs_sample_neighbors: rng_key = rng_seed;
+ * dgs_sample_blocks hop l: rng_seed + 0x9E3779B97F4A7C15 * (l + 1)). */
+int dgs_debug_ares_keys(const float *weights, int64_t deg, uint64_t rng_key, uint64_t item,
+                        float *keys_out, void *stream);
+
 /* Whole mini-batch: num_layers hops (fan_out walked from the back, like the reference's
  * sampler.cc:20 and DGL), each hop sampled and relabelled: out_row / out_col are positions in
  * out_frontier[l], hop l+1's seeds are hop l's frontier.  One cooperative launch, all enqueued
@@ -265,10 +276,12 @@ int dgs_frontier_heat(int itype, int etype, const void *seeds, int64_t n, const 
 
 /* ------------------------------------------------------------------ block construction
  * CSC row pointer of a sampled hop: replaces what dgl.create_block((coo_col, coo_row), ...) derives
- * in the caller (example/graphsage/node_classification.py:18-28).  `sorted_rows` = the hop's coo_row
- * (ascending - every sampling entry point emits it so); indptr gets num_rows + 1 entries of the id
- * type.  *unsorted_flag_dev (optional, zeroed by the caller) is set to 1 if the rows are not
- * ascending or out of range. */
+ * in the caller (example/graphsage/node_classification.py:18-28).  `sorted_rows` = the hop's coo_row,
+ * ascending.  Precondition: the sampling entry points emit ascending rows when the hop's seeds are
+ * DISTINCT (always from the second hop on); a duplicate seed of hop 0 is relabelled to its first
+ * occurrence and breaks the order - pass unsorted_flag_dev then.  indptr gets num_rows + 1 entries of
+ * the id type.  *unsorted_flag_dev (optional, zeroed by the caller) is set to 1 if the rows are not
+ * ascending or out of range (entries of indptr covered by the violating runs are then unwritten). */
 int dgs_coo_rows_to_indptr(int itype, const void *sorted_rows, int64_t nnz, int64_t num_rows,
                            void *indptr, int *unsorted_flag_dev, void *stream);
 

@@ -137,6 +137,27 @@ def main():
     dist.barrier()
     fs.close()
 
+    # ---- "selfish" placement: every rank caches the SAME hot nodes (get_cache_nids_selfish), so the
+    # all-gathered lists hold world * n ids but only n distinct keys - the table is sized for n
+    # (hashmap.cu:20) and every hit must resolve to the local rank
+    deg_all = ip[1:] - ip[:-1]
+    hot = torch.argsort(deg_all, descending=True)[:N // 3]
+    fs = dgs.classes.P2PCacheFeatureServer(fp, hot.to(dev), rank)
+    assert fs._mod_world == 0
+    assert torch.equal(fs._CAPI_get_feature(q).cpu(), feat[q.cpu()])
+    ok, oi, od = fs._CAPI_get_local_cache_hashmap_tensors()
+    live = ok >= 0
+    assert int(live.sum()) == hot.numel() and bool((od[live] == rank).all())
+    smp = dgs.classes.P2PCacheSampler(ipp, ixp, torch.Tensor(), hot, rank)
+    out = smp._CAPI_sample_node_classifiction(seeds, [-1, -1], False)
+    exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(ip), t2n(ix), 2)
+    for a, e in zip(out, exp):
+        for x, z in zip(a, e):
+            assert np.array_equal(t2n(x), z)
+    smp.close()
+    dist.barrier()
+    fs.close()
+
     # ---- exact modulo sharding (node n on GPU n % world, slot n // world): arithmetic owner, no
     # location table; shards generated directly on the device (from_device_shard[s] extensions)
     nids, sp, si, spr = dgs_synth.make_shard(N, E, rank, world, seed=31, device=dev, weights=True, classes=8)

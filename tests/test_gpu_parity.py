@@ -131,6 +131,42 @@ def test_loc_table_lookup_matches_oracle(dgs, cuda, P):
         assert (t2n(i2)[t2n(k2) < 0] == -1).all() and (t2n(d2)[t2n(k2) < 0] == -1).all()
 
 
+@pytest.mark.parametrize("P", [4, 8])
+def test_loc_table_identical_cache_lists(dgs, cuda, P):
+    """Every rank caches the SAME hot nodes (what get_cache_nids_selfish / the "selfish" policy
+    produce): sum(counts) = P * n but only n distinct keys, which is what the reference sizes the
+    table for (hashmap.cu:20; Update() overwrites, hashmap.h:18-32).  The build must accept it and
+    resolve every id to the local rank."""
+    from dgs import _lib
+    from dgs._util import ptr, stream
+    lib = _lib.lib()
+    N, n = 100000, 20000
+    rng = np.random.default_rng(P)
+    hot = rng.choice(N, n, replace=False)
+    cap = lib.dgs_loc_table_capacity(n)
+    assert P * n > cap                     # 80 000 / 160 000 listed ids > 65 536 slots, 20 000 distinct
+    dl = [torch.from_numpy(hot).to(cuda) for _ in range(P)]
+    q = rng.integers(0, N, 50000)
+    qd = torch.from_numpy(q).to(cuda)
+    for rank in (0, P - 1):
+        table = torch.empty(2 * cap, dtype=torch.int64, device=cuda)
+        _lib.check(lib.dgs_loc_table_build(ptr(table), cap, 1, P, rank, _lib.vp_array([ptr(t) for t in dl]),
+                                           _lib.i64_array([n] * P), stream()))
+        od, oi = torch.empty_like(qd), torch.empty_like(qd)
+        _lib.check(lib.dgs_loc_table_lookup(ptr(table), cap, 1, ptr(qd), len(q), ptr(od), ptr(oi), stream()))
+        key, idx, dev = oracle.hashmap_build([hot] * P, rank, n)
+        ed, ei = oracle.hashmap_lookup(key, idx, dev, q)
+        assert np.array_equal(t2n(od), ed) and np.array_equal(t2n(oi), ei)
+        assert set(t2n(od).tolist()) <= {-1, rank}
+    # too many DISTINCT ids for the capacity is still an error (reported, not a hang)
+    many = [torch.arange(i * 3000, (i + 1) * 3000, device=cuda) for i in range(4)]
+    small = lib.dgs_loc_table_capacity(4000)      # 8192 slots < 12 000 distinct ids
+    table = torch.empty(2 * small, dtype=torch.int64, device=cuda)
+    rc = lib.dgs_loc_table_build(ptr(table), small, 1, 4, 0, _lib.vp_array([ptr(t) for t in many]),
+                                 _lib.i64_array([3000] * 4), stream())
+    assert rc != 0 and b"distinct" in lib.dgs_last_error()
+
+
 @pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("P,rank", [(1, 0), (2, 1), (4, 2), (8, 7)])
 def test_extract_p2p_virtual_ranks_bit_exact(dgs, cuda, P, rank, algo):
@@ -399,6 +435,131 @@ def test_biased_without_replacement_matches_ares_reference(dgs, cuda):
     assert chi2 < df + 6 * np.sqrt(2 * df), chi2
     per_seed = col.reshape(copies, k).sort(dim=1).values
     assert (per_seed[:, 1:] != per_seed[:, :-1]).all()
+
+
+# ------------------------------------------------------------------ biased sampling: EXACT check
+GOLDEN = 0x9E3779B97F4A7C15
+M64 = (1 << 64) - 1
+
+
+def _ares_graph(N=30000, seed=0):
+    """Node n has deg_n DISTINCT neighbours (n * 1009 + t) % N, t < deg_n, so a returned id tells the
+    position t that was picked.  Degrees cover the copy path (<= k), one-pass rows (<= 512 weights),
+    multi-pass rows (513, 2 000) and hub rows shared by the whole CTA in the fused kernel (20 000)."""
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.randint(5, 60, (N,), generator=g)
+    special = {11: 40, 12: 513, 13: 2000, 14: 20000, 15: 512, 16: 1024, 17: 33, 18: 4097}
+    for n, d in special.items():
+        deg[n] = d
+    indptr = torch.zeros(N + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(deg, 0)
+    owner = torch.repeat_interleave(torch.arange(N), deg)
+    t = torch.arange(int(indptr[-1])) - indptr[owner]
+    indices = (owner * 1009 + t) % N
+    w = (torch.randn(indices.numel(), generator=g).abs() + 1e-3).float()
+    return indptr, indices, w, sorted(special)
+
+
+def _expected_ares(dgs, w_dev, indptr, nid, k, key, item):
+    b, e = int(indptr[nid]), int(indptr[nid + 1])
+    keys = dgs.ops._Test_AresKeys(w_dev[b:e], key, item)
+    # k largest keys, ties broken by the smaller position: a stable descending sort
+    order = torch.sort(keys, descending=True, stable=True).indices
+    return order[:k].cpu()
+
+
+def _check_ares_hop(dgs, w_dev, indptr, N, seed_ids, picked_ids_per_seed, k, key, ordered):
+    for i, (nid, got_ids) in enumerate(zip(seed_ids, picked_ids_per_seed)):
+        deg = int(indptr[nid + 1] - indptr[nid])
+        pos = (got_ids - nid * 1009) % N
+        if deg <= k:
+            assert pos.tolist() == list(range(deg))                        # copy path, CSR order
+            continue
+        exp = _expected_ares(dgs, w_dev, indptr, nid, k, key, i)
+        if ordered:
+            assert pos.tolist() == exp.tolist(), (nid, deg, k)
+        else:
+            assert sorted(pos.tolist()) == sorted(exp.tolist()), (nid, deg, k)
+
+
+@pytest.mark.parametrize("k", [10, 25, 32, 40, 70])
+def test_biased_without_replacement_exact_topk(dgs, cuda, k):
+    """Weighted sampling without replacement IS the top-k of the A-Res keys log2(u_t) / w_t
+    (rowwise_sampling_bias.cu:111-132), and the keys are a pure function of (launch key, seed index,
+    edge position).  So every selection path can be checked EXACTLY against a top-k of the keys
+    (dgs_debug_ares_keys): the per-hop op (warp per seed: threshold -> collect -> tighten passes for
+    rows > 512 weights; replace-the-minimum reservoir for k > 32) and the fused batch kernel
+    (CTA-shared hub rows, cross-warp merge).  k <= 32: picks come out in descending key order (set
+    AND order compared); k > 32: reservoir order is unspecified (set compared)."""
+    N = 30000
+    indptr, indices, w, special = _ares_graph(N)
+    ip, ix, wd = indptr.to(cuda), indices.to(cuda), w.to(cuda)
+    g = torch.Generator().manual_seed(k)
+    others = torch.randperm(N - 100, generator=g)[:700] + 100
+    seeds = torch.cat([torch.tensor(special), others])
+    seeds = seeds[torch.randperm(seeds.numel(), generator=g)]
+    R = 0x1234567 + k
+    # ---- per-hop op: launch key = rng_seed, item = seed position
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds.to(cuda), ip, ix, wd, k, False, rng_seed=R)
+    cnt = torch.clamp(indptr[seeds + 1] - indptr[seeds], max=k)
+    per_seed = torch.split(col.cpu(), cnt.tolist())
+    assert torch.equal(row.cpu(), torch.repeat_interleave(seeds, cnt))
+    _check_ares_hop(dgs, wd, indptr, N, seeds.tolist(), per_seed, k, R, ordered=k <= 32)
+    # ---- fused batch kernel, two hops: hop l uses key rng_seed + GOLDEN * (l + 1), item = position
+    # of the seed in that hop's seed list (hop 1's seeds = hop 0's frontier)
+    smp = dgs.classes.CSRSampler(ip, ix, wd)
+    k2 = 10 if k > 10 else 25
+    out = smp._pipe.sample(seeds.to(cuda), [k2, k], False, R)     # fan-out walked from the back
+    cur = seeds
+    for l, ((s_, f_, r_, c_), kk) in enumerate(zip(out, (k, k2))):
+        assert torch.equal(s_.cpu(), cur)
+        f = f_.cpu()
+        cnt = torch.clamp(indptr[cur + 1] - indptr[cur], max=kk)
+        assert torch.equal(r_.cpu(), torch.repeat_interleave(torch.arange(cur.numel()), cnt))
+        per_seed = torch.split(f[c_.cpu()], cnt.tolist())
+        key = (R + GOLDEN * (l + 1)) & M64
+        # hop 1 has ~10^4 seeds: check the special rows wherever they appear + a sample of the rest
+        idx = list(range(cur.numel())) if l == 0 else \
+            [i for i, n in enumerate(cur.tolist()) if n in special] + list(range(0, cur.numel(), 37))
+        for i in idx:
+            nid = int(cur[i])
+            deg = int(indptr[nid + 1] - indptr[nid])
+            pos = (per_seed[i] - nid * 1009) % N
+            if deg <= kk:
+                assert pos.tolist() == list(range(deg))
+                continue
+            exp = _expected_ares(dgs, wd, indptr, nid, kk, key, i)
+            if kk <= 32:
+                assert pos.tolist() == exp.tolist(), (l, nid, deg, kk)
+            else:
+                assert sorted(pos.tolist()) == sorted(exp.tolist()), (l, nid, deg, kk)
+        cur = f
+
+
+def test_biased_k1_and_replace_follow_weights_long_row(dgs, cuda):
+    """deg 2 000 (four 512-weight passes per row): k = 1 w/o replacement and k = 7 with replacement
+    must follow w_i / sum(w); chi-square over 2 000 cells, 6-sigma bound.  Through the per-hop op and
+    through the fused batch kernel."""
+    deg, copies = 2000, 30000
+    g = torch.Generator().manual_seed(deg)
+    w = (torch.rand(deg, generator=g) * 3 + 0.05).float()
+    indptr, indices, probs = _star_graph(deg, copies, cuda, w)
+    seeds = torch.arange(copies, device=cuda)
+    pw = (w / w.sum()).double().numpy()
+    df = deg - 1
+    bound = df + 6 * np.sqrt(2 * df)
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds, indptr, indices, probs, 1, False, rng_seed=3)
+    counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    assert _chi2(counts, copies * pw) < bound
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds, indptr, indices, probs, 7, True, rng_seed=11)
+    counts = torch.bincount(col, minlength=deg).double().cpu().numpy()
+    assert _chi2(counts, copies * 7 * pw) < bound
+    # fused kernel (num_nodes = copies; neighbour ids < deg <= copies)
+    smp = dgs.classes.CSRSampler(indptr, indices, probs)
+    for k, rep, rs in ((1, False, 5), (7, True, 6)):
+        (s_, f_, r_, c_), = smp._CAPI_sample_node_classifiction(seeds, [k], rep, rng_seed=rs)
+        counts = torch.bincount(f_[c_], minlength=deg).double().cpu().numpy()[:deg]
+        assert _chi2(counts, copies * k * pw) < bound
 
 
 # ------------------------------------------------------------------ relabel (bit-exact)
