@@ -11,13 +11,21 @@ extract of the input frontier, on synthetic graphs of the named shapes (dist-gnn
 
 N = 1  : BASELINE configs[1] - products-shaped graph resident in HBM, uniform [15,10,5], batch
          1024, un-cached path (CSRSampler + _CAPI_cuda_index_select).
-N > 1  : the same shape sharded over the N GPUs of the box (node n lives on GPU n mod N: CSR rows
-         and feature rows), every rank samples its own seed batches through P2PCacheSampler /
-         P2PCacheFeatureServer; remote rows are NVLink peer loads issued inside the kernels, no
-         collective on the data path ("scaling": "weak").
+N > 1  : the north-star layout - the same shape SHARDED over the N GPUs of the box (node n lives on
+         GPU n mod N: CSR rows and feature rows), every rank samples its own seed batches through
+         P2PCacheSampler / P2PCacheFeatureServer; remote rows are NVLink peer loads issued inside
+         the kernels, no collective on the data path ("scaling": "weak").  The full-replica layout
+         the cache policy would pick on a 180 GB GPU is measured too and reported as the extra key
+         `replica_layout` (--layout policy / replica make it the headline instead).
+Every BASELINE config is reachable: --shape papers100M|friendster (shards are generated on their
+owner GPU), --bias --fan-out 25,10 --cache-ratio r (config 3), --replicate-hot f.
+Before anything is timed every rank checks one full-neighbour batch against the CPU oracle and one
+extract against the closed-form feature rows ("parity_checked").
 One JSON line is printed by rank 0.
 """
 import argparse
+import glob
+import importlib.util
 import json
 import os
 import subprocess
@@ -34,6 +42,7 @@ import torch  # noqa: E402
 
 METRIC = "sampled_edges_per_sec"
 UNIT = "edges/s"
+BIG_SHAPES = ("papers100M", "friendster")   # never materialised on the host / on one rank's CPU
 
 
 def parse_args():
@@ -42,18 +51,36 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shape", default="products", choices=["tiny", "small", "products"])
-    ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--fan-out", default="15,10,5")
-    ap.add_argument("--bias", action="store_true")
+    ap.add_argument("--shape", default="products",
+                    choices=["tiny", "small", "products", "papers100M", "friendster"])
+    ap.add_argument("--batch", type=int, default=None, help="default 1024 (4096 for friendster)")
+    ap.add_argument("--fan-out", default=None,
+                    help="default 15,10,5 (25,10 with --bias, 20,15,10 for friendster)")
+    ap.add_argument("--bias", action="store_true", help="edge-weight biased sampling")
+    ap.add_argument("--cache-ratio", type=float, default=None,
+                    help="N = 1: cache the top r*N nodes by degree on the GPU (location table), read "
+                         "the rest from pinned host memory; 0 = everything from pinned host memory; "
+                         "default: graph resident in HBM, un-cached ops path")
     ap.add_argument("--extract-algo", type=int, default=0)
-    ap.add_argument("--layout", default="policy", choices=["policy", "sharded"],
-                    help="N > 1: where graph + feature rows live. policy = placement computed by "
-                         "DistGNN.cache (the reference's selfish / selfless / auto model) for the free "
-                         "HBM; sharded = node n on GPU n mod N, remote rows over NVLink")
+    ap.add_argument("--layout", default="sharded", choices=["sharded", "policy", "replica"],
+                    help="N > 1: where graph + feature rows live.  sharded = node n on GPU n mod N, "
+                         "remote rows over NVLink (north star); policy = placement computed by "
+                         "DistGNN.cache for the free HBM; replica = everything on every GPU")
+    ap.add_argument("--replicate-hot", type=float, default=0.0,
+                    help="sharded layout: additionally cache the feature rows of the top FRAC nodes by "
+                         "degree on every GPU (local hits replace NVLink reads; location table)")
+    ap.add_argument("--prefetch", type=int, default=8,
+                    help="mini-batches per launch of the pipelined leg (e2e_pipelined)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-extra-layout", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 4096 if args.shape == "friendster" else 1024
+    if args.fan_out is None:
+        args.fan_out = "20,15,10" if args.shape == "friendster" else ("25,10" if args.bias else "15,10,5")
+    return args
 
 
 def peaks():
@@ -119,20 +146,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_name(args, fan_out):
+def config_of(args, fan_out):
+    """The `config` object - a pure function of the command line, so both arms print the same one."""
     import dgs_synth
     N, E, D, dt = dgs_synth.SHAPES[args.shape]
-    return (f"{args.shape}-shaped synthetic graph ({N} nodes, ~{E} edges, {D}-dim "
-            f"{str(dt).replace('torch.', '')} feats), {'biased' if args.bias else 'uniform'} fan-out "
-            f"{fan_out}, batch {args.batch}")
+    row_bytes = D * torch.empty(0, dtype=dt).element_size()
+    w = (f"{args.shape}-shaped synthetic graph ({N} nodes, ~{E} edges, {D}-dim "
+         f"{str(dt).replace('torch.', '')} feats), {'biased' if args.bias else 'uniform'} fan-out "
+         f"{fan_out}, batch {args.batch}")
+    if args.cache_ratio is not None:
+        w += f", GPU cache of the top {args.cache_ratio:g} of the nodes by degree, rest in pinned host memory"
+    return {"workload": w,
+            "l2": "inputs larger than L2 (feature table %.2f GB, CSR %.2f GB, fresh seeds every step)"
+                  % (N * row_bytes / 1e9, (E * 8 + N * 8) / 1e9)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ---------------------------------------------------------------------------------- CPU arm
 def cpu_baseline(args, fan_out, host_graph, seconds, steps=None, warmup=2):
-    """DGL-semantics CPU sample_neighbors + relabel + index_select (oracle port), all host threads."""
-    import numpy as np
+    """DGL-semantics CPU sample_neighbors + relabel + index_select (oracle port), all host threads
+    (asked for explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     import oracle
     import dgs_synth
+    oracle.set_num_threads(0)
+    torch.set_num_threads(host_cores())
     indptr, indices, probs, feat = host_graph
     N = len(indptr) - 1
     runner = oracle.CpuBatchRunner(indptr, indices, probs, feat, args.batch, fan_out)
@@ -162,8 +205,8 @@ def cpu_baseline(args, fan_out, host_graph, seconds, steps=None, warmup=2):
             "ms_per_step": el / done * 1e3, "steps": done}
 
 
-def host_graph_from(args, device):
-    """Generate the graph once (on the GPU when there is one) and hand numpy copies to the CPU arm."""
+def full_graph(args, device):
+    """The whole graph on one device (small shapes) - also the source of the CPU arm's numpy copies."""
     import dgs_synth
     N, E, D, dt = dgs_synth.SHAPES[args.shape]
     indptr, indices, probs = dgs_synth.make_csr(N, E, seed=0, device=device, weights=args.bias)
@@ -171,27 +214,151 @@ def host_graph_from(args, device):
     return indptr, indices, probs, feat
 
 
+def to_host_numpy(ip, ix, pr, ft):
+    f = ft.cpu()
+    if f.dtype == torch.bfloat16:      # numpy has no bf16: rows are moved as bytes anyway
+        f = f.view(torch.int16)
+    return (ip.cpu().numpy(), ix.cpu().numpy(), pr.cpu().numpy() if pr is not None else None, f.numpy())
+
+
+def host_ram_ok(args):
+    import dgs_synth
+    N, E, D, dt = dgs_synth.SHAPES[args.shape]
+    need = N * D * torch.empty(0, dtype=dt).element_size() + E * (12 if args.bias else 8) + N * 8
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 1.5 * need, need
+    except Exception:
+        return False, need
+
+
 def run_reference(args, fan_out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.shape in BIG_SHAPES:
+        ok, need = host_ram_ok(args)
+        if not ok:
+            emit({"impl": "reference", "unavailable": f"{args.shape}: the CPU arm needs the whole graph "
+                                                     f"({need / 1e9:.0f} GB) in host memory"})
+            return
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    ip, ix, pr, ft = host_graph_from(args, dev)
-    host = (ip.cpu().numpy(), ix.cpu().numpy(), pr.cpu().numpy() if pr is not None else None,
-            ft.cpu().numpy())
-    del ip, ix, pr, ft
+    host = to_host_numpy(*full_graph(args, dev))
+    if dev == "cuda":
+        torch.cuda.empty_cache()
     cb = cpu_baseline(args, fan_out, host, None, steps=args.steps, warmup=max(1, args.warmup))
     line = {
         "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
         "warmup": max(1, args.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "impl": "reference", "config": {"workload": workload_name(args, fan_out)},
+        "impl": "reference", "config": config_of(args, fan_out),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "batches_per_sec": cb["batches_per_sec"], "extract_gbps": cb["extract_gbps"],
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------- reference kernels
+def load_reference_module():
+    """oracle/_ref: the UNMODIFIED reference compiled for sm_100a (oracle/build_ref.sh).  Its module
+    is also called `dgs`, so this repo's package is hidden from sys.modules while it loads."""
+    cands = glob.glob(os.path.join(ROOT, "oracle", "_ref", "dgs.cpython-*.so"))
+    if not cands:
+        raise RuntimeError("oracle/_ref not built (oracle/build_ref.sh needs /root/reference)")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "dgs" or k.startswith("dgs.")}
+    try:
+        spec = importlib.util.spec_from_file_location("dgs", cands[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k in list(sys.modules):
+            if k == "dgs" or k.startswith("dgs."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    return mod
+
+
+def reference_gpu_leg(args, fan_out, ipc, ixc, prc, ftc, seeds_dev, steps, dev):
+    """The reference's own kernels on this B200, same inputs, same plugin calls (P2PCacheSampler +
+    P2PCacheFeatureServer with every node cached on the GPU = the best case for the reference).
+    Outside every timed region of this repo's arm; reported like cpu_baseline."""
+    ref = load_reference_module()
+    ref.ops._CAPI_set_nccl(1, ref.ops._CAPI_get_unique_id(), 0)
+    N = ipc.numel() - 1
+    allnodes = torch.arange(N)
+    smp = ref.classes.P2PCacheSampler(ipc, ixc, prc, allnodes, 0)
+    fs = ref.classes.P2PCacheFeatureServer(ftc, allnodes.to(dev), 0)
+    for i in range(3):
+        b = smp._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+        fs._CAPI_get_feature(b[-1][1])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges = rows = 0
+    e0.record()
+    for i in range(steps):
+        b = smp._CAPI_sample_node_classifiction(seeds_dev[3 + i], fan_out, False)
+        x = fs._CAPI_get_feature(b[-1][1])
+        edges += sum(t[2].numel() for t in b)
+        rows += x.shape[0]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    row_bytes = ftc.shape[1] * ftc.element_size()
+    del smp, fs
+    torch.cuda.empty_cache()
+    return {"value": edges / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "batches_per_sec": steps / (ms * 1e-3),
+            "extract_gbps": rows * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
+            "what": "oracle/_ref = the unmodified reference sources compiled for sm_100a, same B200, "
+                    "same seeds; sampler._CAPI_sample_node_classifiction + feature_server._CAPI_get_"
+                    "feature with every node cached on the GPU (src/sampling/sampler.cc:146-166, "
+                    "src/feature/cuda/feature_ops.cu:75-138)"}
+
+
+# ---------------------------------------------------------------------------------- parity (untimed)
+def parity_check(args, sampler, extract, N, D, dt, dev, rank, host_csr, shard_info):
+    """One full-neighbour batch against the CPU oracle and one extract against the closed-form
+    feature rows, on every rank, before anything is timed."""
+    import numpy as np
+    import oracle
+    import dgs_synth
+    g = torch.Generator().manual_seed(4242 + rank)
+    seeds = torch.randint(0, N, (48,), generator=g).unique()
+    if host_csr is not None:
+        ip, ix = host_csr
+        hops = 2
+    else:
+        # big shapes: rebuild the CSR rows of the seeds from the closed-form generators and hand the
+        # oracle a CSR in which only those rows are populated (one hop)
+        E = dgs_synth.SHAPES[args.shape][1]
+        deg = dgs_synth.degrees(N, E, device=dev)
+        gptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(deg, 0, out=gptr[1:])
+        order = torch.sort(seeds).values.to(dev)
+        d = deg[order]
+        starts = gptr[order]
+        sparse = torch.zeros(N, dtype=torch.int64, device=dev)
+        sparse[order] = d
+        ipd = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(sparse, 0, out=ipd[1:])
+        rows = [dgs_synth.edge_targets(N, 0, int(s), int(c), device=dev) for s, c in
+                zip(starts.tolist(), d.tolist())]
+        ix = torch.cat(rows).cpu().numpy() if rows else np.zeros(0, np.int64)
+        ip = ipd.cpu().numpy()
+        del deg, gptr, sparse, ipd
+        hops = 1
+    exp = oracle.sample_blocks_all_neighbors(seeds.numpy(), ip, ix, hops)
+    got = sampler._CAPI_sample_node_classifiction(seeds.to(dev), [-1] * hops, False)
+    ok = len(got) == len(exp)
+    for a, e in zip(got, exp):
+        for x, z in zip(a, e):
+            ok = ok and np.array_equal(x.cpu().numpy(), z)
+    q = torch.randint(0, N, (20000,), generator=g).to(dev)
+    x = extract(q)
+    ok = ok and torch.equal(x, dgs_synth.feature_rows(q, D, dt))
+    return bool(ok)
 
 
 # ---------------------------------------------------------------------------------- B200 arm
@@ -213,63 +380,156 @@ def run_b200(args, fan_out):
 
     N, E, D, dt = dgs_synth.SHAPES[args.shape]
     K, W = args.steps, args.warmup
-    ip, ix, pr, ft = host_graph_from(args, dev)
-    row_bytes = D * ft.element_size()
+    row_bytes = D * torch.empty(0, dtype=dt).element_size()
+    big = args.shape in BIG_SHAPES
     labels = (torch.arange(N, device=dev) % 47).to(torch.int64)
-    host_graph = None
-    if rank == 0 and not args.no_cpu_baseline:
-        host_graph = (ip.cpu().numpy(), ix.cpu().numpy(), pr.cpu().numpy() if pr is not None else None,
-                      ft.cpu().numpy())
+    host_graph = host_csr = None
+    policy = None
+    closers = []
+    ipc = ixc = prc = ftc = None
 
-    if world == 1:
-        sampler = dgs.classes.CSRSampler(ip, ix, pr)
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-        def extract(nids):
-            return dgs.ops._CAPI_cuda_index_select(ft, nids, args.extract_algo)
-        layout = "graph + features resident in HBM, un-cached path"
-    else:
-        # The class API wants the whole graph as pinned CPU tensors (src/sampling/sampler.cc:64-86);
-        # the products shape is small enough for that.
-        ipc, ixc, ftc = ip.cpu().pin_memory(), ix.cpu().pin_memory(), ft.cpu().pin_memory()
-        prc = pr.cpu().pin_memory() if pr is not None else torch.Tensor()
-        del ip, ix, ft
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM,
+                               "min": dist.ReduceOp.MIN}[op])
+        return float(t.item())
+
+    # ------------------------------------------------------------------ data + samplers
+    feature_source = None     # tensor or P2PCacheFeatureServer handed to BatchLoader
+    if big:
+        # shards are generated on their owner GPU; nothing whole-graph ever exists on the host
+        t0 = time.time()
+        nids, sp, si, spr = dgs_synth.make_shard(N, E, rank, world, device=dev, weights=args.bias)
+        feat = dgs_synth.make_features(N, D, dt, device=dev, nids=nids)
+        torch.cuda.synchronize()
+        sampler = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, spr, nids, N, rank)
+        fnids = nids
+        if args.replicate_hot > 0 and world > 1:
+            deg = dgs_synth.degrees(N, E, device=dev)
+            hot = torch.topk(deg, int(N * args.replicate_hot)).indices
+            del deg
+            extra = hot[hot % world != rank]
+            feat = torch.cat([feat, dgs_synth.make_features(N, D, dt, device=dev, nids=extra)])
+            fnids = torch.cat([nids, extra.to(nids.dtype)])
+        fserver = dgs.classes.P2PCacheFeatureServer.from_device_shard(feat, fnids, N, rank)
+        del sp, si, spr, feat
         torch.cuda.empty_cache()
-        shard_nids = torch.arange(rank, N, world, dtype=torch.int64)   # node n -> GPU n mod world
-        policy = None
-        if args.layout == "policy":
-            # what the reference's training script does (example/graphsage/node_classification.py:
-            # 73-167): heat of every node -> value per byte -> knapsack over the free device memory
-            from DistGNN.cache import choose_cache_policy, get_available_memory, get_node_heat
-            graph = {"indptr": ipc, "indices": ixc, "features": ftc}
-            if pr is not None:
-                graph["probs"] = prc
-            sh, fh = get_node_heat(ipc, ixc, torch.arange(N), fan_out,
-                                   probs=prc if pr is not None else None, mode="uva")
-            free = get_available_memory(local_rank, 7 << 30)
-            name, s_nids, f_nids = choose_cache_policy(graph, sh, fh, free, world,
-                                                       probs="probs" if pr is not None else None)
-            del sh, fh
-            policy = {"chosen": name, "free_hbm_gb": free / 1e9,
-                      "structure_nodes_cached": int(s_nids.numel()),
-                      "feature_rows_cached": int(f_nids.numel())}
-            s_nids, f_nids = torch.sort(s_nids.cpu())[0], torch.sort(f_nids.cpu())[0]
-        else:
-            s_nids = f_nids = shard_nids
-        sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, s_nids, rank)
-        fserver = dgs.classes.P2PCacheFeatureServer(ftc, f_nids, rank)
+        closers += [sampler, fserver]
+        feature_source = fserver
+        layout = (f"CSR + features sharded nid mod {world} over {world} GPU(s), shards generated on "
+                  f"the device ({time.time() - t0:.0f} s)" +
+                  (", NVLink peer loads in-kernel" if world > 1 else ""))
+        if args.replicate_hot > 0 and world > 1:
+            layout += f", feature rows of the top {args.replicate_hot:g} nodes by degree replicated"
 
-        def extract(nids):
-            return fserver._CAPI_get_feature(nids, args.extract_algo)
-        if sampler._mod_world < 0 and fserver._mod_world < 0:
-            layout = (f"placement by the cache policy ({policy['chosen']}): everything fits the free HBM, "
-                      f"so every GPU holds a full replica (CSR + features); no remote reads")
-        elif sampler._mod_world > 0:
-            layout = f"CSR + features sharded nid mod {world} over {world} GPUs, NVLink peer loads in-kernel"
+        def extract(nids_):
+            return fserver._CAPI_get_feature(nids_, args.extract_algo)
+    else:
+        ip, ix, pr, ft = full_graph(args, dev)
+        need_host = (rank == 0 and not args.no_cpu_baseline) or world > 1 or args.cache_ratio is not None
+        if need_host:
+            ipc, ixc, ftc = ip.cpu().pin_memory(), ix.cpu().pin_memory(), ft.cpu().pin_memory()
+            prc = pr.cpu().pin_memory() if pr is not None else torch.Tensor()
+            host_csr = (ipc.numpy(), ixc.numpy())
+            if rank == 0 and not args.no_cpu_baseline:
+                f = ftc.view(torch.int16) if ftc.dtype == torch.bfloat16 else ftc
+                host_graph = (ipc.numpy(), ixc.numpy(), prc.numpy() if pr is not None else None, f.numpy())
         else:
-            layout = f"placement by the cache policy ({policy['chosen']}), location table, NVLink peer loads"
+            host_csr = (ip.cpu().numpy(), ix.cpu().numpy())
+        if world == 1 and args.cache_ratio is None:
+            sampler = dgs.classes.CSRSampler(ip, ix, pr)
+            feature_source = ft
+            layout = "graph + features resident in HBM, un-cached path"
+
+            def extract(nids_):
+                return dgs.ops._CAPI_cuda_index_select(ft, nids_, args.extract_algo)
+        elif world == 1:
+            del ip, ix, ft
+            torch.cuda.empty_cache()
+            if args.cache_ratio <= 0:
+                sampler = dgs.classes.CSRSampler(ipc, ixc, prc if pr is not None else None, device=dev)
+                feature_source = ftc
+                layout = "graph + features in pinned host memory (UVA reads over PCIe), nothing cached"
+
+                def extract(nids_):
+                    return dgs.ops._CAPI_cuda_index_select(ftc, nids_, args.extract_algo)
+            else:
+                from DistGNN.cache import get_cache_nids_by_degree
+                cache = get_cache_nids_by_degree(ipc, args.cache_ratio)
+                sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, cache, 0)
+                fserver = dgs.classes.P2PCacheFeatureServer(ftc, cache, 0)
+                closers += [sampler, fserver]
+                feature_source = fserver
+                layout = (f"top {args.cache_ratio:g} of the nodes by degree ({cache.numel()}) cached in HBM "
+                          f"behind the location table, the rest read from pinned host memory")
+
+                def extract(nids_):
+                    return fserver._CAPI_get_feature(nids_, args.extract_algo)
+        else:
+            # The class API wants the whole graph as pinned CPU tensors (src/sampling/sampler.cc:64-86)
+            del ip, ix, ft
+            torch.cuda.empty_cache()
+            shard_nids = torch.arange(rank, N, world, dtype=torch.int64)   # node n -> GPU n mod world
+            if args.layout == "policy":
+                # what the reference's training script does (example/graphsage/node_classification.py:
+                # 73-167): heat of every node -> value per byte -> knapsack over the free device memory
+                from DistGNN.cache import choose_cache_policy, get_available_memory, get_node_heat
+                graph = {"indptr": ipc, "indices": ixc, "features": ftc}
+                if pr is not None:
+                    graph["probs"] = prc
+                sh, fh = get_node_heat(ipc, ixc, torch.arange(N), fan_out,
+                                       probs=prc if pr is not None else None, mode="uva")
+                free = get_available_memory(local_rank, 7 << 30)
+                name, s_nids, f_nids = choose_cache_policy(graph, sh, fh, free, world,
+                                                           probs="probs" if pr is not None else None)
+                del sh, fh
+                policy = {"chosen": name, "free_hbm_gb": free / 1e9,
+                          "structure_nodes_cached": int(s_nids.numel()),
+                          "feature_rows_cached": int(f_nids.numel())}
+                s_nids, f_nids = torch.sort(s_nids.cpu())[0], torch.sort(f_nids.cpu())[0]
+            elif args.layout == "replica":
+                s_nids = f_nids = torch.arange(N, dtype=torch.int64)
+            else:
+                s_nids = f_nids = shard_nids
+                if args.replicate_hot > 0:
+                    from DistGNN.cache import get_cache_nids_by_degree
+                    hot = get_cache_nids_by_degree(ipc, args.replicate_hot)
+                    f_nids = torch.cat([shard_nids, hot[hot % world != rank]])
+            sampler = dgs.classes.P2PCacheSampler(ipc, ixc, prc, s_nids, rank)
+            fserver = dgs.classes.P2PCacheFeatureServer(ftc, f_nids, rank)
+            closers += [sampler, fserver]
+            feature_source = fserver
+
+            def extract(nids_):
+                return fserver._CAPI_get_feature(nids_, args.extract_algo)
+            if sampler._mod_world < 0 and fserver._mod_world < 0:
+                layout = ("every GPU holds a full replica (CSR + features)" +
+                          (f" - placement by the cache policy ({policy['chosen']}): everything fits the "
+                           f"free HBM" if policy else "") + "; no remote reads")
+            elif sampler._mod_world > 0:
+                layout = f"CSR + features sharded nid mod {world} over {world} GPUs, NVLink peer loads in-kernel"
+                if args.replicate_hot > 0:
+                    layout += (f", feature rows of the top {args.replicate_hot:g} nodes by degree "
+                               f"replicated on every GPU (location table)")
+            else:
+                layout = f"placement by the cache policy ({policy['chosen']}), location table, NVLink peer loads"
+
+    # ------------------------------------------------------------------ parity before timing
+    ok = parity_check(args, sampler, extract, N, D, dt, dev, rank, host_csr, None)
+    parity_checked = reduce(1.0 if ok else 0.0, "min") == 1.0
+    assert parity_checked, "parity check failed: blocks / extract differ from the oracle"
 
     # distinct seed batches per rank and per step
-    seeds_all = dgs_synth.seed_batches(N, args.batch, 3 * (K + W) + 2, seed=rank)
+    n_batches = 3 * (K + W) + 2 + max(1, args.prefetch) * (K + W + 2)
+    seeds_all = dgs_synth.seed_batches(N, args.batch, n_batches, seed=rank)
     seeds_dev = seeds_all.to(dev)
     seeds_pin = seeds_all.pin_memory()
 
@@ -289,7 +549,7 @@ def run_b200(args, fan_out):
         torch.cuda.current_stream().synchronize()
         return blocks, x
 
-    loader = dgs.classes.BatchLoader(sampler, ft if world == 1 else fserver, labels)
+    loader = dgs.classes.BatchLoader(sampler, feature_source, labels)
 
     def step_fused(i):
         # extension: same batch through ONE call / one host round trip (dgs.classes.BatchLoader)
@@ -297,25 +557,23 @@ def run_b200(args, fan_out):
                                    labels_out=lab_host)
         return blocks, x
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def timed(step, first, count):
+        """`count` steps between two CUDA events + barriers; max over ranks, sums over ranks."""
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        edges = rows = hop_seeds = uniq = 0
+        barrier()
+        e0.record()
+        for i in range(first, first + count):
+            blocks, x = step(i)
+            edges += sum(b[2].numel() for b in blocks)
+            hop_seeds += sum(b[0].numel() for b in blocks)
+            uniq += sum(b[1].numel() for b in blocks)
+            rows += x.shape[0]
+        e1.record()
+        barrier()
+        return {"ms": reduce(e0.elapsed_time(e1), "max"), "edges": reduce(edges, "sum"),
+                "rows": reduce(rows, "sum"), "local": (edges, rows, hop_seeds, uniq)}
 
     # ---- device-resident timing ("value")
     for i in range(2):   # set-up (allocator pools, lazily enabled peer mappings) - not a timed step
@@ -327,30 +585,17 @@ def run_b200(args, fan_out):
         clocks.start()
     for i in range(W):
         step_device(i)
-    barrier()
     launches0 = dgs.launch_count()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    edges = rows = hop_seeds = uniq = 0
-    e0.record()
-    for i in range(W, W + K):
-        blocks, x = step_device(i)
-        edges += sum(b[2].numel() for b in blocks)
-        hop_seeds += sum(b[0].numel() for b in blocks)
-        uniq += sum(b[1].numel() for b in blocks)
-        rows += x.shape[0]
-    e1.record()
-    barrier()
+    t_dev = timed(step_device, W, K)
     launches = dgs.launch_count() - launches0
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    total_edges = sum_over_ranks(edges)
-    total_rows = sum_over_ranks(rows)
-    # ---- roofline of the dominant kernel (the extract gather): the K launches of the timed region
-    # are re-issued back to back on the same stream between two CUDA events, so the figure is the
-    # kernel's own average duration (no host gaps); every launch gathers a different random
-    # 75+ MB row set out of the 0.98 GB table into its own output buffer.
-    # (the frontiers are re-sampled here and copied out of their arenas: holding arena views inside
-    # the timed loop would force a fresh cudaMalloc per step)
+    ms = t_dev["ms"]
+    edges, rows, hop_seeds, uniq = t_dev["local"]
+
+    # ---- roofline of the two kernels: the K launches of the timed region are re-issued back to back
+    # on the same stream between two CUDA events, so the figure is the kernel's own average duration
+    # (no host gaps); every launch gathers a different random 75+ MB row set out of the table into
+    # its own output buffer.  (the frontiers are re-sampled here and copied out of their arenas:
+    # holding arena views inside the timed loop would force a fresh cudaMalloc per step)
     frontiers = [sampler._CAPI_sample_node_classifiction(seeds_dev[W + i], fan_out, False)[-1][1].clone()
                  for i in range(K)]
     outs = [extract(f) for f in frontiers]   # untimed pass: the caching allocator now owns K outputs
@@ -365,7 +610,9 @@ def run_b200(args, fan_out):
     x1.record()
     torch.cuda.synchronize()
     ex_ms = x0.elapsed_time(x1)
-    ex_bytes = sum(f.numel() * (2 * row_bytes + 8) for f in frontiers)
+    ex_ms_max = reduce(ex_ms, "max")
+    ex_rows = sum(f.numel() for f in frontiers)
+    ex_bytes = ex_rows * (2 * row_bytes + 8)
     del outs
     # same for the sampling kernel (one cooperative launch per batch): K batches back to back
     pipe = sampler._pipe
@@ -378,79 +625,86 @@ def run_b200(args, fan_out):
     sm_ms = x0.elapsed_time(x1)
     del keep
     # SURVEY 8d, summed over hops: sampling 24 (S + nnz) + relabel 8 (S + nnz) + 32 nnz + 8 U
+    # (+ 4 bytes per weight of every sampled row when biased: not counted - conservative)
     sm_bytes = 24.0 * (hop_seeds + edges) + 8.0 * (hop_seeds + edges) + 32.0 * edges + 8.0 * uniq
 
     # ---- end-to-end timing through the plugin API with host seeds / host result ("e2e")
     for i in range(W):
         step_e2e(K + W + i)
-    barrier()
-    t_edges = 0
-    e0.record()
-    for i in range(K + 2 * W, 2 * K + 2 * W):
-        blocks, x = step_e2e(i)
-        t_edges += sum(b[2].numel() for b in blocks)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_edges = sum_over_ranks(t_edges)
+    t_e2e = timed(step_e2e, K + 2 * W, K)
 
     # ---- the same end-to-end step through the one-call BatchLoader extension ("e2e_fused")
     for i in range(W):
         step_fused(2 * K + 2 * W + i)
-    barrier()
-    f_edges = 0
-    e0.record()
-    for i in range(2 * K + 3 * W, 3 * K + 3 * W):
-        blocks, x = step_fused(i)
-        f_edges += sum(b[2].numel() for b in blocks)
-    e1.record()
-    barrier()
-    ms_fused = max_over_ranks(e0.elapsed_time(e1))
-    fused_edges = sum_over_ranks(f_edges)
-    clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through both timed regions
+    t_fused = timed(step_fused, 2 * K + 3 * W, K)
 
-    # ---- N > 1, policy placement: the same steps over the modulo-sharded layout as well (north star
-    # item 4: remote CSR rows and feature rows read by NVLink peer loads inside the kernels)
-    sharded = None
-    if world > 1 and args.layout == "policy":
-        sampler2 = dgs.classes.P2PCacheSampler(ipc, ixc, prc, shard_nids, rank)
-        fserver2 = dgs.classes.P2PCacheFeatureServer(ftc, shard_nids, rank)
-        for i in range(W + 2):
-            b2 = sampler2._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
-            fserver2._CAPI_get_feature(b2[-1][1], args.extract_algo)
+    # ---- B mini-batches per launch ("e2e_pipelined"): the loader takes B seed batches at once
+    pipelined = None
+    B = args.prefetch
+    if B > 1 and hasattr(loader, "load_many"):
+        base = 3 * (K + W) + 2
+        groups = [seeds_pin[base + j * B: base + (j + 1) * B] for j in range(K + W + 2)]
+
+        def step_many(j):
+            res = loader.load_many(groups[j], fan_out, False, algo=args.extract_algo)
+            blocks = [b for r in res for b in r[0]]
+            x = torch.empty(sum(r[1].shape[0] for r in res), 0)
+            return blocks, x
+        for j in range(W + 2):
+            step_many(j)
+        t_many = timed(step_many, W + 2, K)
+        pipelined = {"value": t_many["edges"] / (t_many["ms"] * 1e-3), "unit": UNIT,
+                     "batches_per_launch": B, "ms_per_batch": t_many["ms"] / (K * B),
+                     "batches_per_sec": world * K * B / (t_many["ms"] * 1e-3),
+                     "extract_gbps": t_many["rows"] * (2 * row_bytes + 8) / (t_many["ms"] * 1e-3) / 1e9,
+                     "note": "extension: BatchLoader.load_many - B seed batches from pinned host memory "
+                             "sampled by ONE cooperative launch (the hops of all B batches share every "
+                             "phase and grid barrier), then B extracts; results bit-identical to B "
+                             "single calls with the same RNG seeds"}
+        # the multi-batch sampling kernel alone, back to back
+        sd = [g.to(dev) for g in groups[:K + 2]]
+        keep = [loader.enqueue_many_only(sd[j], fan_out) for j in range(2)]
         barrier()
-        s_edges = s_rows = 0
-        e0.record()
-        for i in range(W, W + K):
-            b2 = sampler2._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
-            x2 = fserver2._CAPI_get_feature(b2[-1][1], args.extract_algo)
-            s_edges += sum(b[2].numel() for b in b2)
-            s_rows += x2.shape[0]
-        e1.record()
-        barrier()
-        ms2 = max_over_ranks(e0.elapsed_time(e1))
-        fr2 = [f.clone() for f in frontiers]
-        outs = [fserver2._CAPI_get_feature(f, args.extract_algo) for f in fr2]
-        del outs
-        barrier()
-        outs = []
         x0.record()
-        for f in fr2:
-            outs.append(fserver2._CAPI_get_feature(f, args.extract_algo))
+        keep = [loader.enqueue_many_only(sd[2 + j], fan_out) for j in range(K)]
         x1.record()
         torch.cuda.synchronize()
-        ex2_ms = max_over_ranks(x0.elapsed_time(x1))
-        del outs
-        tot_e2, tot_r2 = sum_over_ranks(s_edges), sum_over_ranks(s_rows)
-        remote = sum(f.numel() for f in fr2) * row_bytes * (world - 1) / world
-        sharded = {"layout": f"CSR + features sharded nid mod {world}, NVLink peer loads in-kernel",
-                   "value": tot_e2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
-                   "batches_per_sec": world * K / (ms2 * 1e-3),
-                   "extract_avg_launch_ms": ex2_ms / K,
-                   "extract_peer_load_gbps_per_gpu": remote / (ex2_ms * 1e-3) / 1e9,
-                   "nvlink_peak_gbps": 900}
+        pipelined["sample_kernel_ms_per_batch"] = x0.elapsed_time(x1) / (K * B)
+        pipelined["sample_kernel_frac_of_hbm"] = (sm_bytes / K) / (pipelined["sample_kernel_ms_per_batch"]
+                                                                  * 1e-3) / 1e9 / peaks()[0]
+        del keep, sd
+    clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through the timed regions
+
+    # ---- N > 1, sharded headline: the full-replica layout (what the cache policy picks when
+    # everything fits the HBM of every GPU) in the same run, as an extra key
+    extra_layout = None
+    if world > 1 and not big and args.layout == "sharded" and not args.no_extra_layout:
+        everything = torch.arange(N, dtype=torch.int64)
+        sampler2 = dgs.classes.P2PCacheSampler(ipc, ixc, prc, everything, rank)
+        fserver2 = dgs.classes.P2PCacheFeatureServer(ftc, everything, rank)
+
+        def step2(i):
+            b2 = sampler2._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+            return b2, fserver2._CAPI_get_feature(b2[-1][1], args.extract_algo)
+        for i in range(W + 2):
+            step2(i)
+        t2 = timed(step2, W, K)
+        extra_layout = {"layout": "full replica of CSR + features on every GPU, no remote reads",
+                        "value": t2["edges"] / (t2["ms"] * 1e-3), "unit": UNIT, "ms_per_step": t2["ms"] / K,
+                        "batches_per_sec": world * K / (t2["ms"] * 1e-3)}
         sampler2.close()
         fserver2.close()
+
+    # ---- the reference's own kernels on this GPU (N = 1, small shapes), outside the timed regions
+    ref_gpu = None
+    if world == 1 and not big and not args.no_reference_gpu and args.cache_ratio is None:
+        try:
+            if ipc is None:
+                ipc, ixc, ftc = host_csr_to_pinned(host_csr, ft)
+                prc = pr.cpu().pin_memory() if pr is not None else torch.Tensor()
+            ref_gpu = reference_gpu_leg(args, fan_out, ipc, ixc, prc, ftc, seeds_dev, min(K, 20), dev)
+        except Exception as e:   # not built / not loadable on this box: say so, do not fail the bench
+            ref_gpu = {"unavailable": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -458,70 +712,99 @@ def run_b200(args, fan_out):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    remote_frac = 0.0
+    if world > 1 and feature_source is not None and getattr(feature_source, "_mod_world", -1) >= 0:
+        remote_frac = (world - 1) / world
     ex_gbs = ex_bytes / (ex_ms * 1e-3) / 1e9
     sm_gbs = sm_bytes / (sm_ms * 1e-3) / 1e9
-    traffic = {}
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
-        for name, key in (("gather_rows", "extract"), ("fused_batch", "sample")):
-            d = prof[name][0]
-            traffic[key] = (float(d["dram__bytes_read.sum"].split()[0]) +
-                            float(d["dram__bytes_write.sum"].split()[0])) * 1e6
-    except Exception:
-        pass
+    traffic, traffic_src = {}, None
+    for prof_name in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from a committed ncu capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
+            for name, key in (("gather_rows", "extract"), ("fused_batch", "sample")):
+                d = prof[name][0]
+                traffic[key] = (float(d["dram__bytes_read.sum"].split()[0]) +
+                                float(d["dram__bytes_write.sum"].split()[0])) * 1e6
+            traffic_src = (f"profiles/{prof_name} (ncu --set full capture of this kernel on the products "
+                           f"workload, N = 1; a constant read from the file, not measured in this run)")
+            break
+        except Exception:
+            continue
+    if world > 1 or args.shape != "products" or args.bias or args.cache_ratio is not None:
+        traffic, traffic_src = {}, None     # the capture is for the default workload only
     roof_extract = {"bound": "hbm", "kernel": "gather_rows_kernel (feature extract)",
                     "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak,
                     "peak_source": peak_src, "traffic": traffic.get("extract"),
+                    "traffic_source": traffic_src if traffic.get("extract") else None,
                     "algorithmic_bytes": "rows * (2 * row_bytes + 8)", "avg_launch_ms": ex_ms / K,
-                    "rows_per_launch": rows / K}
+                    "rows_per_launch": ex_rows / K}
+    if remote_frac > 0:
+        peer = ex_rows * row_bytes * remote_frac / (ex_ms_max * 1e-3) / 1e9
+        roof_extract.update({"bound": "nvlink", "peer_load_gbps_per_gpu": peer, "nvlink_peak_gbps": 900,
+                             "nvlink_frac": peer / 900.0,
+                             "note": "remote fraction (P-1)/P of the gathered row bytes / slowest "
+                                     "rank's kernel time, against 900 GB/s NVLink ingress per GPU"})
     roof_sample = {"bound": "hbm", "kernel": "fused_batch_kernel (all hops: sample + relabel, one "
                                              "cooperative launch per batch)",
                    "achieved": sm_gbs, "peak": peak, "unit": "GB/s", "frac": sm_gbs / peak,
                    "peak_source": peak_src, "traffic": traffic.get("sample"),
+                   "traffic_source": traffic_src if traffic.get("sample") else None,
                    "algorithmic_bytes": "sum over hops of 24 (S + nnz) [sample] + 8 (S + nnz) + 32 nnz + 8 U [relabel]",
                    "avg_launch_ms": sm_ms / K,
                    "note": "not bandwidth-bound at batch %d: limited by the issue rate of uncoalesced "
-                           "accesses / random atomics and by 9 dependent phases with grid barriers "
-                           "(DESIGN.md section 5, profiles/r01_rt_probe.txt)" % args.batch}
+                           "accesses / random atomics and by dependent phases with grid barriers "
+                           "(DESIGN.md section 5); e2e_pipelined puts B batches in one launch" % args.batch}
     dominant, other = (roof_sample, roof_extract) if sm_ms >= ex_ms else (roof_extract, roof_sample)
     dominant = dict(dominant)
     dominant["share_of_gpu_time"] = max(sm_ms, ex_ms) / (sm_ms + ex_ms)
     line = {
-        "metric": METRIC, "value": total_edges / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": t_dev["edges"] / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": workload_name(args, fan_out), "layout": layout,
-                   "l2": "inputs larger than L2 (feature table %.2f GB, CSR %.2f GB, fresh seeds "
-                         "every step)" % (N * row_bytes / 1e9, (E * 8 + N * 8) / 1e9),
-                   "extract_algo": args.extract_algo},
+        "config": config_of(args, fan_out),
+        "setup": {"layout": layout, "extract_algo": args.extract_algo, "host_cores": host_cores()},
+        "parity_checked": parity_checked,
         "batches_per_sec": world * K / (ms * 1e-3),
-        "extract_gbps": total_rows * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
+        "extract_gbps": t_dev["rows"] * (2 * row_bytes + 8) / (ms * 1e-3) / 1e9,
         "clocks": clk,
-        "e2e": {"value": e2e_edges / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": args.batch * 8, "d2h_bytes_per_step": args.batch * 8 + 48,
-                "ms_per_step": ms_e2e / K, "batches_per_sec": world * K / (ms_e2e * 1e-3),
+        "e2e": {"value": t_e2e["edges"] / (t_e2e["ms"] * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": args.batch * 8, "d2h_bytes_per_step": args.batch * 8 + 16 * len(fan_out),
+                "ms_per_step": t_e2e["ms"] / K, "batches_per_sec": world * K / (t_e2e["ms"] * 1e-3),
                 "note": "seeds from pinned host memory, blocks + features stay on the device (the "
                         "plugin API returns CUDA tensors), labels of the batch + hop sizes read back"},
-        "placement_policy": policy if world > 1 else None,
-        "sharded_layout": sharded,
-        "e2e_fused": {"value": fused_edges / (ms_fused * 1e-3), "unit": UNIT,
-                      "ms_per_step": ms_fused / K, "batches_per_sec": world * K / (ms_fused * 1e-3),
+        "placement_policy": policy,
+        "replica_layout": extra_layout,
+        "e2e_fused": {"value": t_fused["edges"] / (t_fused["ms"] * 1e-3), "unit": UNIT,
+                      "ms_per_step": t_fused["ms"] / K,
+                      "batches_per_sec": world * K / (t_fused["ms"] * 1e-3),
                       "note": "extension, not the reference-facing API: dgs.classes.BatchLoader enqueues "
                               "sample -> extract (frontier size read on the device) -> labels and "
                               "syncs once; same inputs, outputs and copies as e2e"},
+        "e2e_pipelined": pipelined,
         "gpu_launches": launches,
         "roofline": dominant,
         "roofline_other": other,
+        "reference_gpu": ref_gpu,
     }
     if host_graph is not None:
         cb = cpu_baseline(args, fan_out, host_graph, args.cpu_baseline_seconds)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["batches_per_sec"] = cb["batches_per_sec"]
         line["cpu_baseline"]["extract_gbps"] = cb["extract_gbps"]
+    elif big:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port",
+                                "sample": f"skipped: the CPU arm would need the whole {args.shape} graph "
+                                          f"in host memory (run `bench.py --impl reference --shape "
+                                          f"{args.shape}` on a box with enough RAM)"}
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def host_csr_to_pinned(host_csr, ft):
+    ip, ix = host_csr
+    return (torch.from_numpy(ip).pin_memory(), torch.from_numpy(ix).pin_memory(), ft.cpu().pin_memory())
 
 
 class _OnlyJsonOnStdout:

@@ -34,6 +34,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 #include "dgs_common.cuh"
 #include "p2p_server.h"
@@ -390,11 +392,16 @@ struct PosEmit {
 //   B2 thread per slot : neighbour load, padded store, table insert - 8 independent
 //      load -> CAS chains in flight per thread
 // Same RNG counters as the warp-per-seed kernel => identical samples.
-template <typename IdT, typename ET, int MODE>
+// kNoPos (direct tables only): the table slot of an id IS the id, so the slot arrays pos_seed /
+// pos_col are neither written here nor read by the later phases.  ts = seeds per tile; the CTA owns
+// tiles tile0, tile0 + tstride, ...  tagbits: OR-ed into every item index stored in the table
+// (epoch tag of the multi-batch kernel's never-wiped tables; 0 elsewhere).
+template <typename IdT, typename ET, int MODE, bool kNoPos = false>
 __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__restrict__ seeds,
                                                 int64_t S_ub, int64_t S, int k, uint64_t rng_key,
                                                 IdT *__restrict__ pad_col, const HopState &cur,
-                                                uint64_t cap_mask,
+                                                uint64_t cap_mask, int ts, int64_t tile0,
+                                                int64_t tstride, unsigned int tagbits,
                                                 unsigned long long *fine = nullptr) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
   auto fstamp = [&](int slot) {
@@ -414,10 +421,9 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
   unsigned int *s_pick = reinterpret_cast<unsigned int *>(pick_smem);       // [kPkSeeds * k]
   float *s_key = reinterpret_cast<float *>(s_pick + (size_t)kPkSeeds * k);  // [warps * k] (kBias)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ts = pick_tile_seeds(S);
   const int64_t tiles = (S + ts - 1) / ts;
   const bool with_replace = (MODE == kUniformReplace || MODE == kBiasReplace);
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < tiles; tile += tstride) {
     const int64_t i0 = tile * ts;
     const int ns = (int)min((int64_t)ts, S - i0);
     __syncthreads();  // previous tile's readers are done with the shared arrays
@@ -477,7 +483,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
           if (t < k) dst[t] = P[t];
       }
     }
-    if (tile == blockIdx.x) fstamp(1);
+    if (tile == tile0) fstamp(1);
     if (MODE == kUniform && k > kFloydRegs) {
       // random words of Floyd's draws, computed by all threads (one Philox block = 4 draws)
       const int blocks_per_seed = (k + 3) >> 2;
@@ -557,7 +563,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       }
     }
     __syncthreads();
-    if (tile == blockIdx.x) fstamp(2);
+    if (tile == tile0) fstamp(2);
     const int slots = ns * k;
     for (int base = tid; base < slots; base += kBkThreads * kPkBatch) {
       long long v[kPkBatch];
@@ -568,7 +574,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         const int el = base + u * kBkThreads;
         ok[u] = false;
         v[u] = 0;
-        item[u] = (unsigned int)(S_ub + i0 * k + el);
+        item[u] = (unsigned int)(S_ub + i0 * k + el) | tagbits;
         if (el < slots) {
           const int si = el / k;
           const int j = el - si * k;
@@ -590,7 +596,7 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         if (ok[u]) {
           const int64_t e = i0 * k + (base + u * kBkThreads);
           pad_col[e] = (IdT)v[u];
-          cur.pos_col[e] = pos[u];
+          if (!kNoPos) cur.pos_col[e] = pos[u];
         }
       }
     }
@@ -600,88 +606,102 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         seed_prev = atomicCAS(cur.table.key(seed_pos), (unsigned long long)kEmptyKey,
                               (unsigned long long)seed_nid);
       }
-      atomicMin(cur.table.first(seed_pos), (unsigned int)(i0 + tid));
-      cur.pos_seed[i0 + tid] = (unsigned int)seed_pos;
+      atomicMin(cur.table.first(seed_pos), (unsigned int)(i0 + tid) | tagbits);
+      if (!kNoPos) cur.pos_seed[i0 + tid] = (unsigned int)seed_pos;
     }
-    if (tile == blockIdx.x) fstamp(3);
+    if (tile == tile0) fstamp(3);
   }
   fstamp(4);
 }
 
-// Rank phase: CTA per 64 seeds - flags first occurrences among the seeds (A) and the sampled
+// Rank phase, one tile of 128 seeds: flags first occurrences among the seeds (A) and the sampled
 // neighbours (B), counts the edges (C), block scans, per-tile totals to prefA / prefB / prefC.
-__device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k, const HopState &cur,
-                                                 const BlocksWs &ws, bool unique_seeds) {
+// kNoPos: table slot = id, read from seeds / pad_col instead of the slot arrays.
+template <typename IdT, bool kNoPos>
+__device__ __forceinline__ void rank_one_tile(int64_t tile, int64_t S_ub, int64_t S, int k,
+                                              const HopState &cur, const BlocksWs &ws,
+                                              bool unique_seeds, const IdT *__restrict__ seeds,
+                                              const IdT *__restrict__ pad_col,
+                                              unsigned int tagbits = 0) {
   __shared__ long long s_scan[32];
   __shared__ long long s_total;
   __shared__ int s_cnt[kBkTile];
-  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
   const int tid = threadIdx.x;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t i0 = tile * kBkTile;
-    const int ns = (int)min((int64_t)kBkTile, S - i0);
-    const int items = ns * k;
-    const int64_t e0 = i0 * k;
-    __syncthreads();
-    // first wave of loads: seed slot + count, and the first pass of neighbour slots
-    long long fa = 0, c = 0;
-    unsigned int slot_a = 0;
-    if (tid < ns) {
+  const int64_t i0 = tile * kBkTile;
+  const int ns = (int)min((int64_t)kBkTile, S - i0);
+  const int items = ns * k;
+  const int64_t e0 = i0 * k;
+  __syncthreads();
+  // first wave of loads: seed slot + count, and the first pass of neighbour slots
+  long long fa = 0, c = 0;
+  unsigned int slot_a = 0;
+  if (tid < ns) {
+    if (kNoPos) {
+      if (!unique_seeds) slot_a = (unsigned int)ldcg(seeds + i0 + tid);
+    } else {
       slot_a = ldcg(cur.pos_seed + i0 + tid);
-      c = ldcg(cur.cnt + i0 + tid);
-      s_cnt[tid] = (int)c;
     }
-    __syncthreads();
-    // seeds that are a previous frontier are distinct: each is its own first occurrence
-    if (tid < ns)
-      fa = (unique_seeds || ldcg(cur.table.first(slot_a)) == (unsigned int)(i0 + tid)) ? 1 : 0;
-    long long carry = 0;
-    long long totA = 0, totC = 0;
-    for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
-      const int el0 = base + tid * kRkItems;
-      unsigned int slot[kRkItems];
-      bool valid[kRkItems];
-#pragma unroll
-      for (int u = 0; u < kRkItems; ++u) {
-        const int el = el0 + u;
-        valid[u] = false;
-        if (el < items) {
-          const int si = el / k;
-          valid[u] = (el - si * k) < s_cnt[si];
-          if (valid[u]) slot[u] = ldcg(cur.pos_col + e0 + el);
-        }
-      }
-      unsigned int first[kRkItems];
-#pragma unroll
-      for (int u = 0; u < kRkItems; ++u)
-        if (valid[u]) first[u] = ldcg(cur.table.first(slot[u]));
-      if (base == 0) {
-        // A and C share one packed scan (A in the high half)
-        const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
-        totA = s_total >> 32;
-        totC = s_total & 0xffffffffll;
-        if (fa) *cur.table.lrank(slot_a) = (unsigned int)(rac >> 32);
-        if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
-      }
-      int mine = 0;
-      bool fb[kRkItems];
-#pragma unroll
-      for (int u = 0; u < kRkItems; ++u) {
-        fb[u] = valid[u] && first[u] == (unsigned int)(S_ub + e0 + el0 + u);
-        mine += fb[u] ? 1 : 0;
-      }
-      long long r = carry + block_exclusive_scan<long long>((long long)mine, s_scan, &s_total);
-#pragma unroll
-      for (int u = 0; u < kRkItems; ++u)
-        if (fb[u]) *cur.table.lrank(slot[u]) = (unsigned int)(r++);
-      carry += s_total;
-    }
-    if (tid == 0) {
-      ws.prefA[tile] = totA;
-      ws.prefB[tile] = carry;
-      ws.prefC[tile] = totC;
-    }
+    c = ldcg(cur.cnt + i0 + tid);
+    s_cnt[tid] = (int)c;
   }
+  __syncthreads();
+  // seeds that are a previous frontier are distinct: each is its own first occurrence
+  if (tid < ns)
+    fa = (unique_seeds || ldcg(cur.table.first(slot_a)) == ((unsigned int)(i0 + tid) | tagbits)) ? 1 : 0;
+  long long carry = 0;
+  long long totA = 0, totC = 0;
+  for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
+    const int el0 = base + tid * kRkItems;
+    unsigned int slot[kRkItems];
+    bool valid[kRkItems];
+#pragma unroll
+    for (int u = 0; u < kRkItems; ++u) {
+      const int el = el0 + u;
+      valid[u] = false;
+      if (el < items) {
+        const int si = el / k;
+        valid[u] = (el - si * k) < s_cnt[si];
+        if (valid[u])
+          slot[u] = kNoPos ? (unsigned int)ldcg(pad_col + e0 + el) : ldcg(cur.pos_col + e0 + el);
+      }
+    }
+    unsigned int first[kRkItems];
+#pragma unroll
+    for (int u = 0; u < kRkItems; ++u)
+      if (valid[u]) first[u] = ldcg(cur.table.first(slot[u]));
+    if (base == 0) {
+      // A and C share one packed scan (A in the high half)
+      const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
+      totA = s_total >> 32;
+      totC = s_total & 0xffffffffll;
+      if (fa && !(kNoPos && unique_seeds)) *cur.table.lrank(slot_a) = (unsigned int)(rac >> 32);
+      if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
+    }
+    int mine = 0;
+    bool fb[kRkItems];
+#pragma unroll
+    for (int u = 0; u < kRkItems; ++u) {
+      fb[u] = valid[u] && first[u] == ((unsigned int)(S_ub + e0 + el0 + u) | tagbits);
+      mine += fb[u] ? 1 : 0;
+    }
+    long long r = carry + block_exclusive_scan<long long>((long long)mine, s_scan, &s_total);
+#pragma unroll
+    for (int u = 0; u < kRkItems; ++u)
+      if (fb[u]) *cur.table.lrank(slot[u]) = (unsigned int)(r++);
+    carry += s_total;
+  }
+  if (tid == 0) {
+    ws.prefA[tile] = totA;
+    ws.prefB[tile] = carry;
+    ws.prefC[tile] = totC;
+  }
+}
+
+__device__ __forceinline__ void rank_tiles_phase(int64_t S_ub, int64_t S, int k, const HopState &cur,
+                                                 const BlocksWs &ws, bool unique_seeds) {
+  const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    rank_one_tile<long long, false>(tile, S_ub, S, k, cur, ws, unique_seeds, nullptr, nullptr);
 }
 
 // Executed by ONE CTA after every tile total is visible: exclusive scans of the three per-tile
@@ -868,7 +888,8 @@ fused_pick_tile_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
                        int64_t prev_S_ub, const long long *__restrict__ prev_S_dev, int prev_k) {
   const long long pS_live = *prev_S_dev;
   const int64_t S = S_dev ? min(*S_dev, S_ub) : S_ub;
-  pick_tile_phase<IdT, ET, MODE>(g, seeds, S_ub, S, k, rng_key, pad_col, cur, cap_mask);
+  pick_tile_phase<IdT, ET, MODE>(g, seeds, S_ub, S, k, rng_key, pad_col, cur, cap_mask,
+                                 pick_tile_seeds(S), blockIdx.x, gridDim.x, 0u);
   wipe_hop(prev, min((int64_t)pS_live, prev_S_ub), prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
            (int64_t)cap_mask + 1);
 }
@@ -947,8 +968,8 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
     const long long pS_live = ldcg(ws.pending_S);
     const int64_t S = h.S_dev ? min((int64_t)ldcg(h.S_dev), h.S_ub) : h.S_ub;
     pick_tile_phase<IdT, ET, MODE>(g, (const IdT *)h.seeds, h.S_ub, S, h.k, h.key,
-                                   (IdT *)ws.pad_col, cur, a.cap_mask,
-                                   a.trace ? a.trace + 256 + 8 * l : nullptr);
+                                   (IdT *)ws.pad_col, cur, a.cap_mask, pick_tile_seeds(S), blockIdx.x,
+                                   gridDim.x, 0u, a.trace ? a.trace + 256 + 8 * l : nullptr);
     wipe_hop(prev, min((int64_t)pS_live, h.prev_S_ub), h.prev_k, (S + pick_tile_seeds(S) - 1) / pick_tile_seeds(S),
                (int64_t)a.cap_mask + 1);
     stamp();
@@ -1001,6 +1022,406 @@ fused_batch_kernel(GraphSrc g, BlocksWs ws, BatchArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-batch cooperative kernel (direct-addressed relabel tables): B INDEPENDENT mini-batches of
+// the same shape in one launch.  A batch of 1024 seeds cannot fill 148 SMs - the two small hops
+// are pure latency chains (a few dependent round trips + a grid barrier per phase) - so B batches
+// walk through every phase together and share each of the grid barriers; the per-batch cost of a
+// barrier / a dependent round trip drops by B.  Results are bit-identical to B single launches
+// with the same RNG seeds (the RNG is keyed by (batch seed, hop, item), never by geometry).
+//
+// Differences from fused_batch_kernel above (which stays for hashed tables):
+//   * no slot arrays: with direct tables the slot of an id is the id, so pos_seed / pos_col are
+//     gone (one 4-byte store + two 4-byte loads per padded slot less);
+//   * the table is NEVER wiped: an entry is {tag:8 | first item:24, lrank:32} and every use of the
+//     table (one per hop) takes the next smaller tag, so atomicMin makes a newer entry beat any
+//     stale one and a hop only ever reads ids it inserted itself.  One table per batch instead of
+//     two alternating ones, no wipe stores (they were one random store per frontier id - 50 us per
+//     8-batch launch), no epoch argument.  After 255 uses the host clears the table (a memset
+//     every ~85 calls).  Items per hop must fit 24 bits (15.1 M at the friendster config);
+//   * tiles of all batches form one virtual tile space that is dealt round-robin to the CTAs;
+//     the emit phase runs over the concatenated slot space of all batches.
+// Per-batch arrays live at a fixed byte stride (workspace, outputs, counts), so the kernel
+// parameters describe batch 0 only.
+struct MbHop {
+  const void *seeds;                  // batch 0; stride = l == 0 ? seeds_stride : out_stride
+  void *frontier, *out_row, *out_col; // batch 0; stride out_stride
+  int64_t S_ub;
+  int k;
+  int smem_pref;                      // the tile prefixes of all batches fit in shared memory
+};
+struct MbArgs {
+  int L, B;
+  unsigned int tag0;                  // hop l stores / expects tag (tag0 - l) in bits 31..24
+  int64_t seeds_stride, out_stride, ws_stride;   // bytes between consecutive batches
+  long long *counts_dev;              // [B][2 L]  {nnz_0, |frontier_0|, nnz_1, ...}
+  long long *host_counts;             // same layout in mapped pinned host memory (or null)
+  unsigned long long *trace;
+  uint64_t rng[DGS_MAX_BATCHES];
+  MbHop hop[8];
+};
+
+// Per-batch views of the workspace: every array of batch b sits `bo` bytes behind batch 0's.
+// (No dynamic indexing of struct members here - that would push the whole struct to local memory.)
+template <typename T>
+__device__ __forceinline__ T *off_ptr(T *p, int64_t bo) {
+  return (T *)((char *)p + bo);
+}
+__device__ __forceinline__ Tab tab_of(const BlocksWs &w0, int64_t bo) {
+  return Tab{w0.hop[0].table.base + bo, 1};
+}
+constexpr unsigned int kItemMask = 0x00ffffffu;   // low 24 bits of `first`: the item index
+__device__ __forceinline__ BlocksWs ws_of_batch(const BlocksWs &w0, int64_t bo) {
+  BlocksWs w;
+  w.done = off_ptr(w0.done, bo);
+  w.pending_S = nullptr;
+  w.prefA = off_ptr(w0.prefA, bo);
+  w.prefB = off_ptr(w0.prefB, bo);
+  w.prefC = off_ptr(w0.prefC, bo);
+  w.loff = off_ptr(w0.loff, bo);
+  w.pad_col = off_ptr(reinterpret_cast<char *>(w0.pad_col), bo);
+  w.hop[0].cnt = w.hop[1].cnt = off_ptr(w0.hop[0].cnt, bo);
+  w.hop[0].pos_seed = w.hop[1].pos_seed = nullptr;
+  w.hop[0].pos_col = w.hop[1].pos_col = nullptr;
+  w.hop[0].table = w.hop[1].table = Tab{w0.hop[0].table.base + bo, 1};
+  w.cap = w0.cap;
+  w.direct = 1;
+  return w;
+}
+
+// batch that owns virtual index v, given exclusive offsets off[0..B] (off[B] = total)
+__device__ __forceinline__ int batch_of(const long long *off, int B, long long v) {
+  int b = 0;
+  for (int i = 1; i < B; ++i) b += (v >= off[i]) ? 1 : 0;
+  return b;
+}
+
+// Shared-memory scratch of the multi-batch phases.
+struct MbShared {
+  long long S[DGS_MAX_BATCHES];          // live seed count of every batch, this hop
+  long long off[DGS_MAX_BATCHES + 1];    // exclusive offsets (seeds)
+  long long off2[DGS_MAX_BATCHES + 1];   // exclusive offsets (padded slots)
+  bool last;
+};
+
+// live seed counts of hop l into sh.S (every thread of the CTA must call; syncs)
+__device__ __forceinline__ void mb_load_S(const MbArgs &a, int l, MbShared &sh) {
+  __syncthreads();
+  if ((int)threadIdx.x < a.B) {
+    long long S = a.hop[l].S_ub;
+    if (l > 0)
+      S = min((long long)S, ldcg(a.counts_dev + (int64_t)threadIdx.x * 2 * a.L + 2 * (l - 1) + 1));
+    sh.S[threadIdx.x] = S;
+  }
+  __syncthreads();
+}
+
+// ---------------- pick: virtual tiles of all batches, dealt round-robin to the CTAs
+template <typename IdT, typename ET, int MODE>
+__device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, const MbArgs &a, int l,
+                                        MbShared &sh) {
+  const int B = a.B;
+  const int64_t G = gridDim.x;
+  const int k = a.hop[l].k;
+  const int64_t S_ub = a.hop[l].S_ub;
+  const IdT *const seeds0 = (const IdT *)a.hop[l].seeds;
+  const int64_t in_stride = l == 0 ? a.seeds_stride : a.out_stride;
+  const unsigned int tagbits = (a.tag0 - (unsigned int)l) << 24;
+  long long S_total = 0;
+  for (int b = 0; b < B; ++b) S_total += sh.S[b];
+  const int ts = pick_tile_seeds(S_total);
+  long long toff = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t S = sh.S[b];
+    const int64_t tiles = (S + ts - 1) / ts;
+    const int64_t t0 = (((int64_t)blockIdx.x - toff) % G + G) % G;
+    toff += tiles;
+    if (t0 >= tiles) continue;
+    const int64_t bo = (int64_t)b * a.ws_stride;
+    HopState cur;
+    cur.cnt = off_ptr(ws0.hop[0].cnt, bo);
+    cur.pos_seed = nullptr;
+    cur.pos_col = nullptr;
+    cur.table = tab_of(ws0, bo);
+    const uint64_t key = a.rng[b] + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
+    pick_tile_phase<IdT, ET, MODE, true>(
+        g, off_ptr(seeds0, (int64_t)b * in_stride), S_ub, S, k, key,
+        reinterpret_cast<IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)), cur, 0, ts, t0, G,
+        tagbits);
+  }
+}
+
+// ---------------- rank: tiles of 128 seeds; the CTA that finishes a batch's last tile turns that
+// batch's tile totals into exclusive prefixes and publishes its hop sizes
+template <typename IdT>
+__device__ __forceinline__ void mb_rank(const BlocksWs &ws0, const MbArgs &a, int l, MbShared &sh) {
+  const int B = a.B, L = a.L;
+  const int tid = threadIdx.x;
+  const int64_t G = gridDim.x;
+  const int k = a.hop[l].k;
+  const int64_t S_ub = a.hop[l].S_ub;
+  const IdT *const seeds0 = (const IdT *)a.hop[l].seeds;
+  const int64_t in_stride = l == 0 ? a.seeds_stride : a.out_stride;
+  const bool unique_seeds = l > 0;
+  const unsigned int tagbits = (a.tag0 - (unsigned int)l) << 24;
+  long long toff = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t S = sh.S[b];
+    const int64_t tiles = (S + kBkTile - 1) / kBkTile;
+    const int64_t t0 = (((int64_t)blockIdx.x - toff) % G + G) % G;
+    toff += tiles;
+    if (t0 >= tiles) continue;
+    const int64_t bo = (int64_t)b * a.ws_stride;
+    const BlocksWs w = ws_of_batch(ws0, bo);
+    HopState cur;
+    cur.cnt = w.hop[0].cnt;
+    cur.pos_seed = nullptr;
+    cur.pos_col = nullptr;
+    cur.table = tab_of(ws0, bo);
+    const IdT *seeds_b = off_ptr(seeds0, (int64_t)b * in_stride);
+    for (int64_t tile = t0; tile < tiles; tile += G) {
+      rank_one_tile<IdT, true>(tile, S_ub, S, k, cur, w, unique_seeds, seeds_b, (const IdT *)w.pad_col,
+                               tagbits);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) sh.last = (atomicAdd(w.done, 1u) == (unsigned int)(tiles - 1));
+      __syncthreads();
+      if (sh.last) {
+        __threadfence();
+        long long *cd = a.counts_dev + (int64_t)b * 2 * L + 2 * l;
+        rank_tail(S, w, cd, cd + 1);
+        if (tid == 0) *w.done = 0;
+      }
+    }
+  }
+}
+
+// ---------------- emit over the concatenated seed / slot spaces of all batches.  EB = padded slots
+// per thread and pass (independent load chains in flight).
+template <typename IdT, int EB>
+__device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, int l, MbShared &sh,
+                                        unsigned char *dyn_smem) {
+  const int B = a.B;
+  const int tid = threadIdx.x;
+  const int64_t G = gridDim.x;
+  const int k = a.hop[l].k;
+  const int64_t S_ub = a.hop[l].S_ub;
+  const int smem_pref = a.hop[l].smem_pref;
+  const IdT *const seeds0 = (const IdT *)a.hop[l].seeds;
+  IdT *const frontier0 = (IdT *)a.hop[l].frontier;
+  IdT *const row0 = (IdT *)a.hop[l].out_row;
+  IdT *const col0 = (IdT *)a.hop[l].out_col;
+  const bool unique_seeds = l > 0;
+  const int64_t in_stride = l == 0 ? a.seeds_stride : a.out_stride;
+  const int64_t ws_stride = a.ws_stride, out_stride = a.out_stride;
+  // tile prefixes (exclusive, entries [0, tiles]) of every batch: shared-memory copies when they
+  // fit, so the three prefix lookups per slot never leave the SM
+  unsigned int *sp = reinterpret_cast<unsigned int *>(dyn_smem);
+  const int tiles_ub = (int)((S_ub + kBkTile - 1) / kBkTile + 1);   // entries per array
+  if (smem_pref) {
+    for (int b = 0; b < B; ++b) {
+      const int64_t bo = (int64_t)b * ws_stride;
+      const long long *gA = off_ptr(ws0.prefA, bo), *gB = off_ptr(ws0.prefB, bo),
+                      *gC = off_ptr(ws0.prefC, bo);
+      const int n = (int)((sh.S[b] + kBkTile - 1) / kBkTile + 1);
+      unsigned int *pa = sp + (size_t)b * 3 * tiles_ub;
+      for (int t = tid; t < n; t += kBkThreads) {
+        pa[t] = (unsigned int)ldcg(gA + t);
+        pa[tiles_ub + t] = (unsigned int)ldcg(gB + t);
+        pa[2 * tiles_ub + t] = (unsigned int)ldcg(gC + t);
+      }
+    }
+  }
+  if (tid == 0) {
+    long long o1 = 0, o2 = 0;
+    for (int b = 0; b < B; ++b) {
+      sh.off[b] = o1;
+      sh.off2[b] = o2;
+      o1 += sh.S[b];
+      o2 += sh.S[b] * k;
+    }
+    sh.off[B] = o1;
+    sh.off2[B] = o2;
+  }
+  __syncthreads();
+  const int64_t stride = G * kBkThreads;
+  const int64_t gtid = (int64_t)blockIdx.x * kBkThreads + tid;
+  // seeds -> frontier
+  if (unique_seeds) {
+    const int64_t tot = sh.off[B];
+    for (int64_t v0 = gtid; v0 < tot; v0 += stride * 4) {
+      IdT sid[4];
+      int bb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t v = v0 + u * stride;
+        bb[u] = -1;
+        if (v < tot) {
+          bb[u] = batch_of(sh.off, B, v);
+          sid[u] = ldcg(off_ptr(seeds0, (int64_t)bb[u] * in_stride) + (v - sh.off[bb[u]]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (bb[u] >= 0)
+          off_ptr(frontier0, (int64_t)bb[u] * out_stride)[v0 + u * stride - sh.off[bb[u]]] = sid[u];
+    }
+  }
+  for (int64_t v = gtid; !unique_seeds && v < sh.off[B]; v += stride) {
+    const int b = batch_of(sh.off, B, v);
+    const unsigned int i = (unsigned int)(v - sh.off[b]);
+    const IdT sid = ldcg(off_ptr(seeds0, (int64_t)b * in_stride) + i);
+    IdT *frontier = off_ptr(frontier0, (int64_t)b * out_stride);
+    const int64_t bo = (int64_t)b * ws_stride;
+    const int2 fl = tab_of(ws0, bo).first_lrank((uint64_t)sid);
+    if (((unsigned int)fl.x & kItemMask) == i) {
+      const unsigned int pa = smem_pref ? sp[(size_t)b * 3 * tiles_ub + i / kBkTile]
+                                        : (unsigned int)ldcg(off_ptr(ws0.prefA, bo) + i / kBkTile);
+      frontier[pa + (unsigned int)fl.y] = sid;
+    }
+  }
+  // padded slots -> compacted, relabelled COO (+ frontier entries of first occurrences)
+  if (k <= 0) return;
+  const int64_t Etot = sh.off2[B];
+  const unsigned int uk = (unsigned int)k;
+  for (int64_t base = gtid; base < Etot; base += stride * EB) {
+    int bb[EB];
+    unsigned int ee[EB], si[EB];
+    bool ok[EB];
+    IdT cidv[EB], sidv[EB];
+#pragma unroll
+    for (int u = 0; u < EB; ++u) {
+      const int64_t v = base + u * stride;
+      ok[u] = false;
+      if (v < Etot) {
+        const int b = batch_of(sh.off2, B, v);
+        const unsigned int e = (unsigned int)(v - sh.off2[b]);   // < 2^32 (plan)
+        const int64_t bo = (int64_t)b * ws_stride;
+        bb[u] = b;
+        ee[u] = e;
+        si[u] = e / uk;
+        ok[u] = (e - si[u] * uk) < (unsigned int)ldcg(off_ptr(ws0.hop[0].cnt, bo) + si[u]);
+        cidv[u] = ldcg(reinterpret_cast<const IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)) + e);
+        if (!unique_seeds) sidv[u] = ldcg(off_ptr(seeds0, (int64_t)b * in_stride) + si[u]);
+      }
+    }
+    unsigned int cf[EB], cr[EB], sf[EB], sr[EB];
+#pragma unroll
+    for (int u = 0; u < EB; ++u) {
+      if (ok[u]) {
+        const Tab tb = tab_of(ws0, (int64_t)bb[u] * ws_stride);
+        const int2 c2 = tb.first_lrank((uint64_t)cidv[u]);
+        cf[u] = (unsigned int)c2.x & kItemMask; cr[u] = (unsigned int)c2.y;
+        if (!unique_seeds) {
+          const int2 s2 = tb.first_lrank((uint64_t)sidv[u]);
+          sf[u] = (unsigned int)s2.x & kItemMask; sr[u] = (unsigned int)s2.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EB; ++u) {
+      if (ok[u]) {
+        const int b = bb[u];
+        const int64_t bo = (int64_t)b * ws_stride;
+        const unsigned int e = ee[u], s_i = si[u], j = e - s_i * uk;
+        // exclusive tile prefixes of batch b: A (seed first occurrences), B (neighbour first
+        // occurrences), C (edges); entry [tiles] of A = total A
+        const unsigned int *pA = sp + (size_t)b * 3 * tiles_ub;
+        const long long *gA = off_ptr(ws0.prefA, bo), *gB = off_ptr(ws0.prefB, bo),
+                        *gC = off_ptr(ws0.prefC, bo);
+        const int tiles = (int)((sh.S[b] + kBkTile - 1) / kBkTile);
+        auto PA = [&](unsigned int t) { return smem_pref ? pA[t] : (unsigned int)ldcg(gA + t); };
+        auto PB = [&](unsigned int t) { return smem_pref ? pA[tiles_ub + t] : (unsigned int)ldcg(gB + t); };
+        auto PC = [&](unsigned int t) { return smem_pref ? pA[2 * tiles_ub + t] : (unsigned int)ldcg(gC + t); };
+        // new id of the neighbour: first occurrence f among the seeds (< S_ub) or the slots
+        const unsigned int f = cf[u];
+        unsigned int cid;
+        if ((int64_t)f < S_ub)
+          cid = unique_seeds ? f : PA(f / kBkTile) + cr[u];
+        else
+          cid = PA(tiles) + PB((unsigned int)((f - (unsigned int)S_ub) / uk) / kBkTile) + cr[u];
+        if ((int64_t)f == S_ub + (int64_t)e) off_ptr(frontier0, (int64_t)b * out_stride)[cid] = cidv[u];
+        const unsigned int rid = unique_seeds ? s_i : PA(sf[u] / kBkTile) + sr[u];
+        const unsigned int o = PC(s_i / kBkTile) + (unsigned int)ldcg(off_ptr(ws0.loff, bo) + s_i) + j;
+        off_ptr(row0, (int64_t)b * out_stride)[o] = (IdT)rid;
+        off_ptr(col0, (int64_t)b * out_stride)[o] = (IdT)cid;
+      }
+    }
+  }
+}
+
+// ---------------- epilogue: the hop sizes go straight into the caller's pinned host memory (posted
+// PCIe writes): entry 0 is written last, behind a system-scope fence, and is what the host polls.
+// (All sizes are final once the last hop's rank phase is over; other CTAs may still be emitting.)
+__device__ __forceinline__ void mb_deliver_counts(const MbArgs &a) {
+  if (a.host_counts != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int n = 2 * a.L * a.B;
+    for (int i = 1; i < n; ++i) a.host_counts[i] = ldcg(a.counts_dev + i);
+    __threadfence_system();
+    *(volatile long long *)a.host_counts = ldcg(a.counts_dev);
+  }
+}
+
+// One cooperative launch: all hops, phases separated by grid barriers (lowest latency; B = 1).
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads, DGS_COOP_MIN_CTAS)
+multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ MbShared sh;
+  int nt = 0;
+  auto stamp = [&]() {
+    if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[nt++] = t;
+    }
+  };
+  stamp();
+  for (int l = 0; l < a.L; ++l) {
+    mb_load_S(a, l, sh);
+    mb_pick<IdT, ET, MODE>(g, ws0, a, l, sh);
+    stamp();
+    grid.sync();
+    stamp();
+    mb_rank<IdT>(ws0, a, l, sh);
+    stamp();
+    grid.sync();
+    stamp();
+    mb_emit<IdT, kEmBatch>(ws0, a, l, sh, dyn_smem);
+    stamp();
+    if (l + 1 < a.L) grid.sync();   // (nothing follows the last emit)
+    stamp();
+  }
+  mb_deliver_counts(a);
+}
+
+// The same phases as separate kernels (B >= 2): a phase of B batches is throughput work, and a
+// kernel per phase gets its own register budget - the rank and emit phases run at 4 CTAs per SM
+// instead of the 2 the pick phase's registers allow the fused kernel; the kernel boundaries
+// (~3 us each) are shared by the B batches.
+template <typename IdT, typename ET, int MODE>
+__global__ void __launch_bounds__(kBkThreads, 2)
+mb_pick_kernel(GraphSrc g, BlocksWs ws0, MbArgs a, int l) {
+  __shared__ MbShared sh;
+  mb_load_S(a, l, sh);
+  mb_pick<IdT, ET, MODE>(g, ws0, a, l, sh);
+}
+template <typename IdT>
+__global__ void __launch_bounds__(kBkThreads, 4) mb_rank_kernel(BlocksWs ws0, MbArgs a, int l) {
+  __shared__ MbShared sh;
+  mb_load_S(a, l, sh);
+  mb_rank<IdT>(ws0, a, l, sh);
+}
+template <typename IdT>
+__global__ void __launch_bounds__(kBkThreads, 4) mb_emit_kernel(BlocksWs ws0, MbArgs a, int l) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ MbShared sh;
+  mb_load_S(a, l, sh);
+  mb_emit<IdT, 4>(ws0, a, l, sh, dyn_smem);
+  if (l + 1 == a.L) mb_deliver_counts(a);
+}
+
 __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -1008,6 +1429,250 @@ __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {
 }
 
 int build_graph_src(const dgs_graph_t *g, GraphSrc *out);  // sampling.cu
+// ---------------------------------------------------------------------------------------------
+// Workspace plans.  Which kernel a workspace serves is decided when it is sized:
+//   kPathMulti  : multi_batch_kernel - direct tables (node count known), every fan-out fits the
+//                 tile pick phase, <= 8 hops, cooperative launch available; B >= 1 batches;
+//   kPathLegacy : fused_batch_kernel / the 3-kernels-per-hop path (hashed tables, fan-out 0 or
+//                 huge, > 8 hops); one batch.
+// dgs_sample_blocks*_ws_init registers the plan under the workspace pointer; every sampling call
+// looks it up and refuses a workspace that was initialised for something else (a different
+// layout would silently read the relabel tables at the wrong offsets).
+enum { kPathLegacy = 0, kPathMulti = 1 };
+
+struct WsInfo {
+  int path, itype, L, B;
+  int64_t S, num_nodes, bytes;
+  int64_t fan[16];
+  int uses;                  // table uses (hops) since the tables were last cleared (multi path)
+  int64_t *counts_host;      // last pinned pointer asked about ...
+  long long *counts_host_dev;  // ... and its device alias (null: not mapped)
+};
+static std::mutex g_ws_mu;
+static std::unordered_map<const void *, WsInfo> g_ws;
+
+struct MultiPlan {
+  int64_t S_max, E_max, tiles_max, cap, table_bytes, stride, bytes;
+};
+
+static bool coop_launch_supported() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, v = 1;   // no device visible (sizing a workspace on a CPU-only box): assume B200
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) v = 0;
+    cudaGetLastError();
+    cached = v;
+  }
+  return cached == 1;
+}
+
+// can this configuration run on the multi-batch kernel?
+static bool multi_path_ok(int L, const int64_t *fan_out, int64_t num_nodes, int64_t num_seeds) {
+  static const bool no_direct = getenv("DGS_BLOCKS_HASHED") != nullptr;
+  static const char *mode_env = getenv("DGS_BLOCKS_MODE");
+  if (no_direct || (mode_env && strcmp(mode_env, "multi") == 0)) return false;
+  if (L < 1 || L > 8 || !coop_launch_supported()) return false;
+  if (!(num_nodes > 0 && num_nodes < (1ll << 32) - 2 && num_nodes <= (1ll << 29))) return false;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[l];
+    // shared memory of the tile pick phase (weighted case): 128 k positions + 8 k keys
+    if (k <= 0 || (size_t)kPkSeeds * k * sizeof(int) + (size_t)kBkWarps * k * sizeof(float) > 64 * 1024)
+      return false;
+  }
+  // items of a hop (seeds + padded slots) must fit the 24 bits next to the epoch tag
+  int64_t ub = num_seeds < 1 ? 1 : num_seeds;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[L - 1 - l];
+    if (ub + ub * k >= (1ll << 24)) return false;
+    ub += ub * k;
+  }
+  return true;
+}
+
+static int multi_plan(int itype, int B, int64_t num_seeds, int L, const int64_t *fan_out,
+                      int64_t num_nodes, MultiPlan *p, char *base, BlocksWs *ws) {
+  DGS_REQUIRE(B >= 1 && B <= DGS_MAX_BATCHES, "sample_blocks_multi: 1..%d batches per launch",
+              DGS_MAX_BATCHES);
+  int64_t ub = num_seeds < 1 ? 1 : num_seeds, S_max = 1, E_max = 1;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[L - 1 - l];
+    const int64_t e = ub * k;
+    DGS_REQUIRE(ub + e < (1ll << 32) - 2, "sample_blocks: more than 2^32 items in one hop");
+    S_max = std::max(S_max, ub);
+    E_max = std::max(E_max, e);
+    ub += e;
+  }
+  const int idb = itype == DGS_I64 ? 8 : 4;
+  p->S_max = S_max;
+  p->E_max = E_max;
+  p->tiles_max = (S_max + kBkTile - 1) / kBkTile;
+  p->cap = (num_nodes + 1) & ~1ll;
+  p->table_bytes = p->cap * 8;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char *q = base ? base + off : nullptr;
+    off += up256(bytes);
+    return q;
+  };
+  char *done = take(256);
+  char *pa = take((p->tiles_max + 1) * 8), *pb = take((p->tiles_max + 1) * 8),
+       *pc = take((p->tiles_max + 1) * 8);
+  char *cnt = take(S_max * 4);
+  char *loff = take(S_max * 4);
+  char *pad = take(E_max * idb);
+  char *t0 = take(p->table_bytes);
+  p->stride = off;
+  p->bytes = off * B;
+  if (ws) {
+    memset(ws, 0, sizeof(*ws));
+    ws->done = (unsigned int *)done;
+    ws->pending_S = (long long *)(done + 64);
+    ws->prefA = (long long *)pa;
+    ws->prefB = (long long *)pb;
+    ws->prefC = (long long *)pc;
+    ws->loff = (int *)loff;
+    ws->pad_col = pad;
+    for (int b = 0; b < 2; ++b) {
+      ws->hop[b].cnt = (int *)cnt;
+      ws->hop[b].pos_seed = nullptr;
+      ws->hop[b].pos_col = nullptr;
+      ws->hop[b].table.base = t0;
+      ws->hop[b].table.direct = 1;
+    }
+    ws->cap = p->cap;
+    ws->direct = 1;
+  }
+  return 0;
+}
+
+template <typename IdT, typename ET>
+static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t seeds_stride,
+                        int64_t num_seeds, int L, const int64_t *fan_out, int replace,
+                        const uint64_t *rng_seeds, void *const *out_frontier, void *const *out_row,
+                        void *const *out_col, int64_t out_stride, const int64_t *cap_edges,
+                        const int64_t *cap_frontier, int64_t *counts_dev, const BlocksWs &ws,
+                        int64_t ws_stride, long long *host_counts, unsigned int tag0, cudaStream_t st) {
+  const bool bias = src.probs != nullptr || src.sh_probs.p[0] != nullptr;
+  const int mode = bias ? (replace ? kBiasReplace : kBias) : (replace ? kUniformReplace : kUniform);
+  MbArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = L;
+  a.B = B;
+  a.tag0 = tag0;
+  a.seeds_stride = seeds_stride;
+  a.out_stride = out_stride;
+  a.ws_stride = ws_stride;
+  a.counts_dev = (long long *)counts_dev;
+  a.host_counts = host_counts;
+  for (int b = 0; b < B; ++b) a.rng[b] = rng_seeds[b];
+  size_t smem_max = 0;
+  int64_t ub = num_seeds;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k = fan_out[L - 1 - l];
+    DGS_REQUIRE(cap_edges[l] >= ub * k, "sample_blocks: layer %d edge capacity %lld < %lld", l,
+                (long long)cap_edges[l], (long long)(ub * k));
+    DGS_REQUIRE(cap_frontier[l] >= ub * (1 + k), "sample_blocks: layer %d frontier capacity %lld < %lld",
+                l, (long long)cap_frontier[l], (long long)(ub * (1 + k)));
+    MbHop &h = a.hop[l];
+    h.seeds = l == 0 ? (const void *)seeds : out_frontier[l - 1];
+    h.frontier = out_frontier[l];
+    h.out_row = out_row[l];
+    h.out_col = out_col[l];
+    h.S_ub = ub;
+    h.k = (int)k;
+    const size_t sm_pick = (size_t)kPkSeeds * k * sizeof(int) + (mode == kBias ? (size_t)kBkWarps * k * sizeof(float) : 0);
+    const size_t pref_bytes = (size_t)B * 3 * ((size_t)(ub + kBkTile - 1) / kBkTile + 1) * sizeof(unsigned int);
+    static const bool no_smem_pref = getenv("DGS_BLOCKS_GLOBAL_PREFIX") != nullptr;
+    h.smem_pref = (!no_smem_pref && pref_bytes <= 72 * 1024) ? 1 : 0;
+    smem_max = std::max(smem_max, sm_pick);
+    if (h.smem_pref) smem_max = std::max(smem_max, pref_bytes);
+    ub += ub * k;
+  }
+  static const char *split_env = getenv("DGS_MB_SPLIT");   // "0" / "1": force one / many kernels
+  const bool split = split_env ? split_env[0] == '1' : B >= 2;
+  if (split) {
+    // one kernel per phase (see mb_pick_kernel): 3 L launches shared by the B batches
+    size_t pref_max = 0;
+    for (int l = 0; l < L; ++l) {
+      const size_t pref_bytes = (size_t)B * 3 * ((size_t)(a.hop[l].S_ub + kBkTile - 1) / kBkTile + 1) * sizeof(unsigned int);
+      a.hop[l].smem_pref = pref_bytes <= 48 * 1024 ? 1 : 0;     // 4 CTAs per SM
+      if (a.hop[l].smem_pref) pref_max = std::max(pref_max, pref_bytes);
+    }
+    auto kemit = mb_emit_kernel<IdT>;
+    static bool emit_attr_set = false;
+    if (!emit_attr_set) {
+      DGS_CUDA_OK(cudaFuncSetAttribute(kemit, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+      emit_attr_set = true;
+    }
+    const int sms = sm_count();
+    for (int l = 0; l < L; ++l) {
+      const int64_t k = a.hop[l].k, S_ub = a.hop[l].S_ub;
+      const size_t sm_pick = (size_t)kPkSeeds * k * sizeof(int) + (mode == kBias ? (size_t)kBkWarps * k * sizeof(float) : 0);
+#define DGS_MBP(M)                                                                                   \
+  do {                                                                                               \
+    auto kp = mb_pick_kernel<IdT, ET, M>;                                                            \
+    if (sm_pick > 32 * 1024)                                                                         \
+      DGS_CUDA_OK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pick)); \
+    kp<<<sms * 2, kBkThreads, sm_pick, st>>>(src, ws, a, l);                                         \
+  } while (0)
+      switch (mode) {
+        case kUniform: DGS_MBP(kUniform); break;
+        case kUniformReplace: DGS_MBP(kUniformReplace); break;
+        case kBias: DGS_MBP(kBias); break;
+        default: DGS_MBP(kBiasReplace); break;
+      }
+#undef DGS_MBP
+      DGS_LAUNCH_CHECK();
+      const int64_t tiles = (int64_t)B * ((S_ub + kBkTile - 1) / kBkTile);
+      mb_rank_kernel<IdT><<<(int)std::min<int64_t>(tiles, (int64_t)sms * 4), kBkThreads, 0, st>>>(ws, a, l);
+      DGS_LAUNCH_CHECK();
+      const int64_t items = (int64_t)B * (S_ub + S_ub * k);
+      const int64_t ge = (items + kBkThreads * 4 - 1) / (kBkThreads * 4);
+      kemit<<<(int)std::max<int64_t>(1, std::min<int64_t>(ge, (int64_t)sms * 4)), kBkThreads,
+              a.hop[l].smem_pref ? pref_max : 0, st>>>(ws, a, l);
+      DGS_LAUNCH_CHECK();
+    }
+    return 0;
+  }
+  void *kern = nullptr;
+#define DGS_MB(M) kern = (void *)multi_batch_kernel<IdT, ET, M>
+  switch (mode) {
+    case kUniform: DGS_MB(kUniform); break;
+    case kUniformReplace: DGS_MB(kUniformReplace); break;
+    case kBias: DGS_MB(kBias); break;
+    default: DGS_MB(kBiasReplace); break;
+  }
+#undef DGS_MB
+  if (smem_max > 32 * 1024)  // static shared memory (~12 KB) counts against the 48 KB default
+    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  int per_sm = 0;
+  DGS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBkThreads, smem_max));
+  DGS_REQUIRE(per_sm >= 1, "sample_blocks: the batch kernel does not fit an SM (%zu bytes of shared memory)",
+              smem_max);
+  if (per_sm > 4) per_sm = 4;
+  const int grid = sm_count() * per_sm;
+  static const bool trace = getenv("DGS_BLOCKS_TRACE") != nullptr;
+  static unsigned long long *trace_dev = nullptr;
+  if (trace && !trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(unsigned long long));
+  a.trace = trace ? trace_dev : nullptr;
+  GraphSrc src_copy = src;
+  BlocksWs ws_copy = ws;
+  void *params[] = {&src_copy, &ws_copy, &a};
+  DGS_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kBkThreads), params, smem_max, st));
+  dgsb::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (trace) {
+    unsigned long long h[2 + 6 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_dev, sizeof(unsigned long long) * (1 + 6 * L), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[dgs multi trace us, grid %d, B %d] pick sync rank sync emit sync:", grid, B);
+    for (int i = 1; i < 1 + 6 * L; ++i)
+      fprintf(stderr, "%s%.1f", (i - 1) % 6 == 0 ? " | " : " ", (double)(h[i] - h[i - 1]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+  return 0;
+}
+
 
 template <typename IdT, typename ET>
 static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seeds, int L,
@@ -1246,11 +1911,114 @@ static int launch_blocks(const GraphSrc &src, const IdT *seeds, int64_t num_seed
 
 using namespace dgsb;
 
+static void ws_register(const void *ws, int path, int itype, int B, int64_t S, int L,
+                        const int64_t *fan_out, int64_t num_nodes, int64_t bytes) {
+  WsInfo w;
+  memset(&w, 0, sizeof(w));
+  w.path = path;
+  w.itype = itype;
+  w.B = B;
+  w.S = S;
+  w.L = L;
+  w.num_nodes = num_nodes;
+  w.bytes = bytes;
+  for (int l = 0; l < L && l < 16; ++l) w.fan[l] = fan_out[l];
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  g_ws[ws] = w;
+}
+
+// The plan a workspace was initialised for; checks the call against it.  exact_seeds: the legacy
+// layout depends on the seed count itself; the multi layout only needs num_seeds <= the init value.
+static int ws_lookup(const void *ws, int itype, int B, int64_t num_seeds, int L, const int64_t *fan_out,
+                     int64_t num_nodes, int64_t ws_bytes, WsInfo *out) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_ws.find(ws);
+  DGS_REQUIRE(it != g_ws.end(), "sample_blocks: workspace %p was never initialised with "
+              "dgs_sample_blocks_ws_init / dgs_sample_blocks_multi_ws_init", ws);
+  const WsInfo &w = it->second;
+  bool same = w.itype == itype && w.L == L && w.num_nodes == num_nodes && B <= w.B && B >= 1;
+  for (int l = 0; same && l < L; ++l) same = w.fan[l] == fan_out[l];
+  same = same && (w.path == kPathMulti ? num_seeds <= w.S : num_seeds == w.S);
+  DGS_REQUIRE(same, "sample_blocks: workspace was initialised for another configuration (itype %d, "
+              "%d batch(es) of %lld seeds, %d layers, %lld nodes) - the call asks for itype %d, %d x "
+              "%lld seeds, %d layers, %lld nodes or another fan-out", w.itype, w.B, (long long)w.S,
+              w.L, (long long)w.num_nodes, itype, B, (long long)num_seeds, L, (long long)num_nodes);
+  DGS_REQUIRE(ws_bytes >= w.bytes, "sample_blocks: workspace %lld < %lld bytes", (long long)ws_bytes,
+              (long long)w.bytes);
+  *out = w;
+  return 0;
+}
+
+// Device alias of a pinned + mapped host buffer (null when the kernel cannot write it); the answer
+// is remembered per workspace.
+static long long *mapped_alias(const void *ws, int64_t *counts_host) {
+  static const bool no_direct = getenv("DGS_BLOCKS_COUNTS_MEMCPY") != nullptr;
+  if (no_direct || counts_host == nullptr) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    auto it = g_ws.find(ws);
+    if (it != g_ws.end() && it->second.counts_host == counts_host) return it->second.counts_host_dev;
+  }
+  cudaPointerAttributes at;
+  void *dp = nullptr;
+  long long *alias = nullptr;
+  if (cudaPointerGetAttributes(&at, counts_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+      cudaHostGetDevicePointer(&dp, counts_host, 0) == cudaSuccess)
+    alias = (long long *)dp;
+  cudaGetLastError();
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_ws.find(ws);
+  if (it != g_ws.end()) {
+    it->second.counts_host = counts_host;
+    it->second.counts_host_dev = alias;
+  }
+  return alias;
+}
+
+extern "C" int64_t dgs_sample_blocks_multi_ws_bytes(int itype, int num_batches, int64_t num_seeds,
+                                                    int num_layers, const int64_t *fan_out,
+                                                    int64_t num_nodes) {
+  if (!fan_out || !multi_path_ok(num_layers, fan_out, num_nodes, num_seeds)) {
+    set_error("sample_blocks_multi: this configuration needs the single-batch path (unknown node "
+              "count, fan-out 0 / too large for the tile phase, > 8 hops or no cooperative launch)");
+    return -1;
+  }
+  MultiPlan p;
+  if (multi_plan(itype, num_batches, num_seeds, num_layers, fan_out, num_nodes, &p, nullptr, nullptr))
+    return -1;
+  return p.bytes;
+}
+
+extern "C" int dgs_sample_blocks_multi_ws_init(void *ws, int64_t ws_bytes, int itype, int num_batches,
+                                               int64_t num_seeds, int num_layers,
+                                               const int64_t *fan_out, int64_t num_nodes,
+                                               void *stream) {
+  DGS_REQUIRE(ws && fan_out, "dgs_sample_blocks_multi_ws_init: null argument");
+  DGS_REQUIRE(multi_path_ok(num_layers, fan_out, num_nodes, num_seeds),
+              "dgs_sample_blocks_multi_ws_init: configuration not supported by the multi-batch kernel");
+  MultiPlan p;
+  BlocksWs w;
+  if (multi_plan(itype, num_batches, num_seeds, num_layers, fan_out, num_nodes, &p, (char *)ws, &w))
+    return 1;
+  DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks_multi_ws_init: workspace %lld < %lld bytes",
+              (long long)ws_bytes, (long long)p.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b = 0; b < num_batches; ++b) {
+    char *base = (char *)ws + (int64_t)b * p.stride;
+    DGS_CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
+    DGS_CUDA_OK(cudaMemsetAsync(w.hop[0].table.base + (int64_t)b * p.stride, 0xFF, (size_t)p.table_bytes, st));
+  }
+  ws_register(ws, kPathMulti, itype, num_batches, num_seeds, num_layers, fan_out, num_nodes, p.bytes);
+  return 0;
+}
+
 extern "C" int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
                                               const int64_t *fan_out, int64_t num_nodes) {
+  if (!fan_out) return -1;
+  if (multi_path_ok(num_layers, fan_out, num_nodes, num_seeds))
+    return dgs_sample_blocks_multi_ws_bytes(itype, 1, num_seeds, num_layers, fan_out, num_nodes);
   BlocksPlan p;
-  if (!fan_out || blocks_plan(itype, num_seeds, num_layers, fan_out, num_nodes, &p, nullptr, nullptr))
-    return -1;
+  if (blocks_plan(itype, num_seeds, num_layers, fan_out, num_nodes, &p, nullptr, nullptr)) return -1;
   return p.bytes;
 }
 
@@ -1258,6 +2026,9 @@ extern "C" int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, 
                                          int num_layers, const int64_t *fan_out, int64_t num_nodes,
                                          void *stream) {
   DGS_REQUIRE(ws && fan_out, "dgs_sample_blocks_ws_init: null argument");
+  if (multi_path_ok(num_layers, fan_out, num_nodes, num_seeds))
+    return dgs_sample_blocks_multi_ws_init(ws, ws_bytes, itype, 1, num_seeds, num_layers, fan_out,
+                                           num_nodes, stream);
   BlocksPlan p;
   BlocksWs w;
   if (blocks_plan(itype, num_seeds, num_layers, fan_out, num_nodes, &p, (char *)ws, &w)) return 1;
@@ -1270,11 +2041,12 @@ extern "C" int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, 
         (int4 *)w.hop[b].table.base, p.table_bytes / 16);
     DGS_LAUNCH_CHECK();
   }
+  ws_register(ws, kPathLegacy, itype, 1, num_seeds, num_layers, fan_out, num_nodes, p.bytes);
   return 0;
 }
 
 // Wait until the hop sizes of the batch enqueued with counts_host have arrived there.
-static int counts_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers, bool by_kernel,
+static int counts_wait(int64_t *counts_host, const int64_t *counts_dev, int64_t n_counts, bool by_kernel,
                        cudaStream_t st) {
   if (by_kernel) {
     volatile int64_t *flag = counts_host;
@@ -1286,9 +2058,54 @@ static int counts_wait(int64_t *counts_host, const int64_t *counts_dev, int num_
     // the stream drained (or failed) without the sizes arriving: take the copy path, which also
     // reports a kernel fault
   }
-  DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * num_layers,
+  DGS_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * n_counts,
                               cudaMemcpyDeviceToHost, st));
   DGS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int sample_multi_impl(const dgs_graph_t *g, int B, const void *seeds, int64_t seeds_stride,
+                             int64_t num_seeds, int num_layers, const int64_t *fan_out, int replace,
+                             const uint64_t *rng_seeds, void *const *out_frontier,
+                             void *const *out_row, void *const *out_col, int64_t out_stride,
+                             const int64_t *cap_edges, const int64_t *cap_frontier,
+                             int64_t *counts_dev, void *ws, int64_t ws_bytes, int64_t *counts_host,
+                             cudaStream_t st, bool wait, const WsInfo &info) {
+  MultiPlan p;
+  BlocksWs w;
+  // the layout is the one the workspace was initialised with (num_seeds may be smaller now)
+  if (multi_plan(g->itype, info.B, info.S, num_layers, fan_out, g->num_nodes, &p, (char *)ws, &w)) return 1;
+  GraphSrc src;
+  if (build_graph_src(g, &src)) return 1;
+  long long *host_dev = mapped_alias(ws, counts_host);
+  if (counts_host && (host_dev || !wait)) *(volatile int64_t *)counts_host = -1;   // sentinel: sizes are >= 0
+  // epoch tags: this call uses the table num_layers times; tags count DOWN from 0xFE so that a
+  // newer entry beats every stale one under atomicMin (0xFF = the cleared state).  Out of tags:
+  // clear the tables (a memset every 255 / L calls) and start over.
+  unsigned int tag0;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    WsInfo &reg = g_ws[ws];
+    if (reg.uses + num_layers > 255) {
+      for (int b = 0; b < info.B; ++b)
+        DGS_CUDA_OK(cudaMemsetAsync(w.hop[0].table.base + (int64_t)b * p.stride, 0xFF,
+                                    (size_t)p.table_bytes, st));
+      reg.uses = 0;
+    }
+    tag0 = 0xFEu - (unsigned int)reg.uses;
+    reg.uses += num_layers;
+  }
+  int rc = 0;
+  DGS_ITYPE_SWITCH(g->itype, IdT, {
+    DGS_ITYPE_SWITCH(g->etype, ET, {
+      rc = launch_multi<IdT, ET>(src, B, (const IdT *)seeds, seeds_stride, num_seeds, num_layers, fan_out,
+                                 replace, rng_seeds, out_frontier, out_row, out_col, out_stride,
+                                 cap_edges, cap_frontier, counts_dev, w, p.stride, host_dev, tag0, st);
+    });
+  });
+  if (rc) return rc;
+  if (counts_host && wait)
+    return counts_wait(counts_host, counts_dev, (int64_t)2 * num_layers * B, host_dev != nullptr, st);
   return 0;
 }
 
@@ -1314,36 +2131,21 @@ static int sample_blocks_impl(const dgs_graph_t *g, const void *seeds, int64_t n
     return 0;
   }
   DGS_REQUIRE(seeds != nullptr, "dgs_sample_blocks: null seeds");
+  DGS_REQUIRE(num_layers >= 1 && num_layers <= 16, "dgs_sample_blocks: 1..16 layers supported");
+  WsInfo info;
+  if (ws_lookup(ws, g->itype, 1, num_seeds, num_layers, fan_out, g->num_nodes, ws_bytes, &info)) return 1;
+  if (info.path == kPathMulti)
+    return sample_multi_impl(g, 1, seeds, 0, num_seeds, num_layers, fan_out, replace, &rng_seed,
+                             out_frontier, out_row, out_col, 0, cap_edges, cap_frontier, counts_dev, ws,
+                             ws_bytes, counts_host, st, wait, info);
   BlocksPlan p;
   BlocksWs w;
   if (blocks_plan(g->itype, num_seeds, num_layers, fan_out, g->num_nodes, &p, (char *)ws, &w)) return 1;
-  DGS_REQUIRE(ws_bytes >= p.bytes, "dgs_sample_blocks: workspace %lld < %lld bytes",
-              (long long)ws_bytes, (long long)p.bytes);
   GraphSrc src;
   if (build_graph_src(g, &src)) return 1;
-  // Can the kernel write the hop sizes into counts_host itself?  (pinned + mapped host memory;
-  // the answer is remembered for the last pointer asked about)
-  long long *host_dev = nullptr;
-  if (counts_host) {
-    static const bool no_direct = getenv("DGS_BLOCKS_COUNTS_MEMCPY") != nullptr;
-    static int64_t *last_host = nullptr;
-    static long long *last_dev = nullptr;
-    if (!no_direct) {
-      if (counts_host != last_host) {
-        cudaPointerAttributes at;
-        void *dp = nullptr;
-        if (cudaPointerGetAttributes(&at, counts_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
-            cudaHostGetDevicePointer(&dp, counts_host, 0) == cudaSuccess)
-          last_dev = (long long *)dp;
-        else
-          last_dev = nullptr;
-        cudaGetLastError();
-        last_host = counts_host;
-      }
-      host_dev = last_dev;
-    }
-    if (host_dev || !wait) *(volatile int64_t *)counts_host = -1;   // sentinel: hop sizes are >= 0
-  }
+  // Can the kernel write the hop sizes into counts_host itself?  (pinned + mapped host memory)
+  long long *host_dev = mapped_alias(ws, counts_host);
+  if (counts_host && (host_dev || !wait)) *(volatile int64_t *)counts_host = -1;   // sentinel: hop sizes are >= 0
   int rc = 0;
   bool by_kernel = false;
   DGS_ITYPE_SWITCH(g->itype, IdT, {
@@ -1359,7 +2161,7 @@ static int sample_blocks_impl(const dgs_graph_t *g, const void *seeds, int64_t n
     // finds the sentinel untouched once the stream has drained and copies the sizes itself)
     if (!wait) return 0;
     // the one host round trip of the batch: hop sizes -> (pinned) host memory
-    return counts_wait(counts_host, counts_dev, num_layers, by_kernel, st);
+    return counts_wait(counts_host, counts_dev, (int64_t)2 * num_layers, by_kernel, st);
   }
   return 0;
 }
@@ -1395,5 +2197,32 @@ extern "C" int dgs_sample_blocks_enqueue(const dgs_graph_t *g, const void *seeds
 extern "C" int dgs_sample_blocks_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers,
                                       void *stream) {
   DGS_REQUIRE(counts_host && counts_dev && num_layers >= 1, "dgs_sample_blocks_wait: bad argument");
-  return counts_wait(counts_host, counts_dev, num_layers, true, (cudaStream_t)stream);
+  return counts_wait(counts_host, counts_dev, (int64_t)2 * num_layers, true, (cudaStream_t)stream);
+}
+
+extern "C" int dgs_sample_blocks_multi(const dgs_graph_t *g, int num_batches, const void *seeds,
+                                       int64_t seeds_stride_bytes, int64_t num_seeds, int num_layers,
+                                       const int64_t *fan_out, int replace, const uint64_t *rng_seeds,
+                                       void *const *out_frontier, void *const *out_row,
+                                       void *const *out_col, int64_t out_stride_bytes,
+                                       const int64_t *cap_edges, const int64_t *cap_frontier,
+                                       int64_t *counts_dev, void *ws, int64_t ws_bytes,
+                                       int64_t *counts_host, int wait, void *stream) {
+  DGS_REQUIRE(g && seeds && fan_out && rng_seeds && out_frontier && out_row && out_col && cap_edges &&
+                  cap_frontier && counts_dev && ws,
+              "dgs_sample_blocks_multi: null argument");
+  DGS_REQUIRE(num_batches >= 1 && num_batches <= DGS_MAX_BATCHES,
+              "dgs_sample_blocks_multi: 1..%d batches per launch", DGS_MAX_BATCHES);
+  DGS_REQUIRE(num_seeds >= 1, "dgs_sample_blocks_multi: empty batches");
+  DGS_REQUIRE(num_layers >= 1 && num_layers <= 8, "dgs_sample_blocks_multi: 1..8 layers supported");
+  DGS_REQUIRE(wait == 0 || counts_host != nullptr, "dgs_sample_blocks_multi: wait needs counts_host");
+  WsInfo info;
+  if (ws_lookup(ws, g->itype, num_batches, num_seeds, num_layers, fan_out, g->num_nodes, ws_bytes, &info))
+    return 1;
+  DGS_REQUIRE(info.path == kPathMulti, "dgs_sample_blocks_multi: workspace was initialised with "
+              "dgs_sample_blocks_ws_init for the single-batch path");
+  return sample_multi_impl(g, num_batches, seeds, seeds_stride_bytes, num_seeds, num_layers, fan_out,
+                           replace, rng_seeds, out_frontier, out_row, out_col, out_stride_bytes, cap_edges,
+                           cap_frontier, counts_dev, ws, ws_bytes, counts_host, (cudaStream_t)stream,
+                           wait != 0, info);
 }

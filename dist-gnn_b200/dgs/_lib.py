@@ -88,6 +88,12 @@ SIGNATURES = {
                                             C.c_uint64, c_vpp, c_vpp, c_vpp, c_i64p, c_i64p, c_vp, c_vp,
                                             c_i64, c_i64, c_vp, c_vp]),
     "dgs_sample_blocks_wait": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
+    "dgs_sample_blocks_multi_ws_bytes": (c_i64, [C.c_int, C.c_int, c_i64, C.c_int, c_i64p, c_i64]),
+    "dgs_sample_blocks_multi_ws_init": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_i64, C.c_int, c_i64p,
+                                                  c_i64, c_vp]),
+    "dgs_sample_blocks_multi": (C.c_int, [C.POINTER(Graph), C.c_int, c_vp, c_i64, c_i64, C.c_int, c_i64p,
+                                          C.c_int, C.POINTER(C.c_uint64), c_vpp, c_vpp, c_vpp, c_i64,
+                                          c_i64p, c_i64p, c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "dgs_relabel_table_capacity": (c_i64, [c_i64]),
     "dgs_relabel_table_bytes": (c_i64, [c_i64]),
     "dgs_relabel_ws_bytes": (c_i64, [c_i64]),

@@ -374,6 +374,132 @@ class _BlockPipeline:
             pl["epoch"] += 1
         return arena
 
+    # ---------------------------------------------------------------- B batches per launch
+    def _plan_many(self, B, S, fan_out):
+        """Workspace + arena layout for B mini-batches of S seeds in one cooperative launch
+        (dgs_sample_blocks_multi); None when the configuration needs the single-batch path."""
+        key = ("many", B, S, tuple(fan_out))
+        pl = self._plans.get(key)
+        if pl is None:
+            l = lib()
+            L = len(fan_out)
+            ubs, nnz_ubs = [], []
+            ub = S
+            for li in range(L):
+                k = fan_out[L - 1 - li]
+                ubs.append(ub)
+                nnz_ubs.append(ub * k)
+                ub = ub + ub * k
+            used = sum(u + 3 * n for u, n in zip(ubs, nnz_ubs))
+            total = (used + 3) & ~3          # per-batch stride: 16-byte aligned for both id widths
+            fo = _lib.i64_array(fan_out)
+            it = ID_DTYPES[self._id_dtype]
+            nbytes = -1
+            if B * total <= MAX_FUSED_ELEMS and all(k > 0 for k in fan_out):
+                nbytes = l.dgs_sample_blocks_multi_ws_bytes(it, B, S, L, fo, self._graph.num_nodes)
+            if nbytes < 0:
+                pl = {"ws": None}
+            else:
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
+                check(l.dgs_sample_blocks_multi_ws_init(ptr(ws), nbytes, it, B, S, L, fo,
+                                                        self._graph.num_nodes, stream()),
+                      "sample_blocks_multi_ws_init")
+                es = torch.empty(0, dtype=self._id_dtype).element_size()
+                offs, off = [], 0
+                for u, n in zip(ubs, nnz_ubs):
+                    offs.append((off, off + u + n, off + u + 2 * n))
+                    off += u + 3 * n
+                counts_host = torch.empty(B * 2 * L, dtype=torch.int64).pin_memory()
+                pl = {"L": L, "B": B, "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "pad": total - used,
+                      "ws": ws, "ws_bytes": int(nbytes), "fo": fo, "es": es, "offs": offs,
+                      "cap_edges": _lib.i64_array(nnz_ubs),
+                      "cap_front": _lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
+                      "a_fr": (C.c_void_p * L)(), "a_row": (C.c_void_p * L)(), "a_col": (C.c_void_p * L)(),
+                      "count_slots": B * 2 * L * 8 // es, "counts_host": counts_host,
+                      "counts_np": counts_host.numpy(), "counts_ptr": counts_host.data_ptr(),
+                      "rng": (C.c_uint64 * B)()}
+            big = pl["ws"] is not None and pl["ws_bytes"] > (1 << 30)
+            if len(self._plans) >= (2 if big else 8):
+                self._plans.clear()
+            self._plans[key] = pl
+        return pl
+
+    def enqueue_many(self, seeds, fan_out, replace=False, rng_seeds=None, deliver_counts=True):
+        """Enqueue B = seeds.shape[0] mini-batches (seeds: [B, S] CUDA tensor) as ONE launch.
+        Returns (plan, arena); arena = B regions of plan["total"] ids, then [B][2 L] int64 counts."""
+        l = lib()
+        fan_out = [int(k) for k in fan_out]
+        B, S = int(seeds.shape[0]), int(seeds.shape[1])
+        pl = self._plan_many(B, S, fan_out)
+        if pl["ws"] is None:
+            raise RuntimeError("enqueue_many: this configuration needs the single-batch path")
+        if rng_seeds is None:
+            rng_seeds = [l.dgs_randn_uint64() for _ in range(B)]
+        for b in range(B):
+            pl["rng"][b] = int(rng_seeds[b]) & 0xFFFFFFFFFFFFFFFF
+        with _on_device(self._device):
+            arena = torch.empty(B * pl["total"] + pl["count_slots"], dtype=seeds.dtype, device=self._device)
+            base, es = arena.data_ptr(), pl["es"]
+            for li, (of, orow, ocol) in enumerate(pl["offs"]):
+                pl["a_fr"][li] = base + of * es
+                pl["a_row"][li] = base + orow * es
+                pl["a_col"][li] = base + ocol * es
+            check(l.dgs_sample_blocks_multi(
+                C.byref(self._graph), B, seeds.data_ptr(), S * es, S, pl["L"], pl["fo"],
+                int(bool(replace)), pl["rng"], pl["a_fr"], pl["a_row"], pl["a_col"], pl["total"] * es,
+                pl["cap_edges"], pl["cap_front"], base + B * pl["total"] * es, pl["ws"].data_ptr(),
+                pl["ws_bytes"], pl["counts_ptr"] if deliver_counts else None, 0, stream()),
+                "sample_blocks_multi")
+        return pl, arena
+
+    def wait_many(self, pl, arena):
+        B = pl["B"]
+        with _on_device(self._device):
+            check(lib().dgs_sample_blocks_wait(pl["counts_ptr"],
+                                               arena.data_ptr() + B * pl["total"] * pl["es"],
+                                               pl["L"] * B, stream()), "sample_blocks_wait")
+
+    def _views_many(self, pl, arena, seeds):
+        """Exact-size views of every batch's blocks from the hop sizes in pl["counts_np"]."""
+        B, L = pl["B"], pl["L"]
+        counts = pl["counts_np"].tolist()
+        sizes = []
+        for b in range(B):
+            for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
+                nnz, nf = counts[b * 2 * L + 2 * li], counts[b * 2 * L + 2 * li + 1]
+                sizes += [nf, u + n - nf, nnz, n - nnz, nnz, n - nnz]
+            sizes.append(pl["pad"])
+        sizes.append(pl["count_slots"])
+        parts = arena.split_with_sizes(sizes)
+        out = []
+        per = 6 * L + 1
+        for b in range(B):
+            cur = seeds[b]
+            blocks = []
+            for li in range(L):
+                frontier = parts[b * per + 6 * li]
+                blocks.append((cur, frontier, parts[b * per + 6 * li + 2], parts[b * per + 6 * li + 4]))
+                cur = frontier
+            out.append(blocks)
+        return out
+
+    def sample_many(self, seeds, fan_out, replace=False, rng_seeds=None):
+        """B mini-batches in one launch: seeds [B, S] (CUDA) -> list of B block lists, each identical
+        to sample(seeds[b], fan_out, replace, rng_seeds[b])."""
+        check_cuda(seeds, "seeds")
+        if seeds.dim() != 2 or seeds.dtype != self._id_dtype:
+            raise RuntimeError("sample_many: seeds must be a [B, S] tensor of the id type of indices")
+        seeds = seeds.contiguous()
+        fan_out = [int(k) for k in fan_out]
+        B = seeds.shape[0]
+        if rng_seeds is None:
+            rng_seeds = [lib().dgs_randn_uint64() for _ in range(B)]
+        if len(fan_out) == 0 or seeds.shape[1] == 0 or self._plan_many(B, seeds.shape[1], fan_out)["ws"] is None:
+            return [self.sample(seeds[b], fan_out, replace, rng_seeds[b]) for b in range(B)]
+        pl, arena = self.enqueue_many(seeds, fan_out, replace, rng_seeds)
+        self.wait_many(pl, arena)
+        return self._views_many(pl, arena, seeds)
+
     def wait_counts(self, pl, arena):
         """Block until the hop sizes of the batch enqueued with deliver_counts=True are in
         pl["counts_np"] (polls the pinned buffer the kernel writes; no stream synchronisation)."""
@@ -414,6 +540,11 @@ class CSRSampler:
 
     def _CAPI_sample_node_classifiction(self, seeds, fan_out, replace=False, rng_seed=None):
         return self._pipe.sample(seeds, fan_out, replace, rng_seed)
+
+    def sample_many(self, seeds, fan_out, replace=False, rng_seeds=None):
+        """Extension: B mini-batches (seeds [B, S]) in ONE cooperative launch; element b equals
+        _CAPI_sample_node_classifiction(seeds[b], fan_out, replace, rng_seeds[b])."""
+        return self._pipe.sample_many(seeds, fan_out, replace, rng_seeds)
 
 
 class P2PCacheSampler:
@@ -533,6 +664,11 @@ class P2PCacheSampler:
         """NodeClassifictionSample (sampler.cc:146-166): list over hops, seed-side hop first, of
         (seeds, frontier, coo_row, coo_col) with coo_* relabelled to positions in frontier."""
         return self._pipe.sample(seeds, fan_out, replace, rng_seed)
+
+    def sample_many(self, seeds, fan_out, replace=False, rng_seeds=None):
+        """Extension: B mini-batches (seeds [B, S]) in ONE cooperative launch; element b equals
+        _CAPI_sample_node_classifiction(seeds[b], fan_out, replace, rng_seeds[b])."""
+        return self._pipe.sample_many(seeds, fan_out, replace, rng_seeds)
 
     def _CAPI_get_cpu_structure_tensors(self):
         """GetCPUStructureTensors (sampler.cc:168-178); probs is None for a uniform sampler (the
@@ -710,6 +846,84 @@ class BatchLoader:
         if labels is not None:
             check_device_readable(labels, "labels")
 
+    def _extract_dyn(self, it, front_ptr, n_ub, nf_dev, out_ptr, algo):
+        """Enqueue the gather of a frontier whose size is still on the device (dgs_extract_dyn)."""
+        l = lib()
+        if self._fs is None or self._fs._mod_world < 0:
+            table = ptr(self._table) if self._fs is None else self._fs.gpu_features_._local_ptr
+            check(l.dgs_extract_dyn(table, None, None, 0, 0, self._row_bytes, it, front_ptr,
+                                    n_ub, nf_dev, out_ptr, int(algo), stream()), "BatchLoader extract")
+        else:
+            fs = self._fs
+            check(l.dgs_extract_dyn(fs._host_ptr, fs.gpu_features_._handle,
+                                    ptr(fs._table) if fs._table is not None else None, fs._cap,
+                                    fs._mod_world, self._row_bytes, it, front_ptr, n_ub, nf_dev,
+                                    out_ptr, int(algo), stream()), "BatchLoader extract")
+
+    def enqueue_many_only(self, seeds, fan_out, replace=False, rng_seeds=None):
+        """bench.py's roofline leg: the B-batch sampling launch alone, no host round trip."""
+        B = seeds.shape[0]
+        return self._pipe.enqueue_many(seeds, fan_out, replace, rng_seeds or list(range(1, B + 1)),
+                                       deliver_counts=False)[1]
+
+    def load_many(self, seeds, fan_out, replace=False, rng_seeds=None, algo=0):
+        """B mini-batches per call: seeds [B, S] (pinned host or CUDA) -> list of B
+        (blocks, features, labels), element b identical to load(seeds[b], ..., rng_seed=rng_seeds[b]).
+        All B batches are sampled by ONE cooperative launch (their hops share every phase and grid
+        barrier), then B extracts and one label gather are enqueued behind it; one host round trip.
+        This is how a training loop that knows its next B seed batches (SeedGenerator) prefetches."""
+        l = lib()
+        fan_out = [int(k) for k in fan_out]
+        L = len(fan_out)
+        if seeds.dim() != 2:
+            raise RuntimeError("load_many: seeds must be [B, S]")
+        B, S = int(seeds.shape[0]), int(seeds.shape[1])
+        if rng_seeds is None:
+            rng_seeds = [l.dgs_randn_uint64() for _ in range(B)]
+        with _on_device(self._device):
+            if not seeds.is_cuda:
+                seeds = seeds.to(self._device, non_blocking=True)     # pinned host -> device, one copy
+            seeds = seeds.contiguous()
+            pl = None
+            if L > 0 and S > 0 and all(k > 0 for k in fan_out):
+                pl = self._pipe._plan_many(B, S, fan_out)
+            if pl is None or pl["ws"] is None:       # single-batch path, B times
+                return [self.load(seeds[b], fan_out, replace, rng_seeds[b], algo) for b in range(B)]
+            pl, arena = self._pipe.enqueue_many(seeds, fan_out, replace, rng_seeds)
+            es, base = pl["es"], arena.data_ptr()
+            counts_ptr = base + B * pl["total"] * es
+            n_max = pl["ubs"][-1] + pl["nnz_ubs"][-1]
+            seen = pl.get("front_seen", 0)
+            n_ub = n_max if seen == 0 else min(n_max, seen + seen // 4 + 1024)
+            x_all = torch.empty((B, n_ub) + self._tail, dtype=self._dtype, device=self._device)
+            it = ID_DTYPES[seeds.dtype]
+            x_stride = n_ub * self._row_bytes
+            for b in range(B):
+                front_ptr = base + (b * pl["total"] + pl["offs"][-1][0]) * es
+                nf_dev = counts_ptr + 8 * (b * 2 * L + 2 * L - 1)
+                self._extract_dyn(it, front_ptr, n_ub, nf_dev, x_all.data_ptr() + b * x_stride, algo)
+            y_all = None
+            if self._labels is not None:
+                y_all = ops._CAPI_cuda_index_select(self._labels, seeds.reshape(-1)).reshape(
+                    (B, S) + tuple(self._labels.shape[1:]))
+            self._pipe.wait_many(pl, arena)
+            blocks_all = self._pipe._views_many(pl, arena, seeds)
+            counts = pl["counts_np"]
+            out = []
+            big = 0
+            for b in range(B):
+                nf = int(counts[b * 2 * L + 2 * L - 1])
+                big = max(big, nf)
+                if nf > n_ub:       # the adaptive bound was too small for this batch
+                    fr = blocks_all[b][-1][1]
+                    x = (ops._CAPI_cuda_index_select(self._table, fr, algo) if self._fs is None
+                         else self._fs._CAPI_get_feature(fr, algo))
+                else:
+                    x = x_all[b, :nf]
+                out.append((blocks_all[b], x, y_all[b] if y_all is not None else None))
+            pl["front_seen"] = max(seen, big)
+        return out
+
     def load(self, seeds, fan_out, replace=False, rng_seed=None, algo=0, labels_out=None):
         """-> (blocks, features of blocks[-1][1], labels of seeds or None).  `labels_out` (pinned host
         tensor) additionally receives the labels inside the same host round trip."""
@@ -739,16 +953,7 @@ class BatchLoader:
             x = torch.empty((n_ub,) + self._tail, dtype=self._dtype, device=self._device)
             it = ID_DTYPES[seeds.dtype]
             nf_dev = counts_ptr + 8 * (2 * L - 1)
-            if self._fs is None or self._fs._mod_world < 0:
-                table = ptr(self._table) if self._fs is None else self._fs.gpu_features_._local_ptr
-                check(l.dgs_extract_dyn(table, None, None, 0, 0, self._row_bytes, it, front_ptr,
-                                        n_ub, nf_dev, ptr(x), int(algo), stream()), "BatchLoader extract")
-            else:
-                fs = self._fs
-                check(l.dgs_extract_dyn(fs._host_ptr, fs.gpu_features_._handle,
-                                        ptr(fs._table) if fs._table is not None else None, fs._cap,
-                                        fs._mod_world, self._row_bytes, it, front_ptr, n_ub, nf_dev,
-                                        ptr(x), int(algo), stream()), "BatchLoader extract")
+            self._extract_dyn(it, front_ptr, n_ub, nf_dev, ptr(x), algo)
             y = ops._CAPI_cuda_index_select(self._labels, seeds) if self._labels is not None else None
             if labels_out is not None and y is not None:
                 labels_out.copy_(y, non_blocking=True)

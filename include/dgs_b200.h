@@ -28,6 +28,7 @@ extern "C" {
 
 #define DGS_B200_ABI_VERSION 2
 #define DGS_MAX_DEVICES 16
+#define DGS_MAX_BATCHES 16 /* mini-batches per dgs_sample_blocks_multi launch */
 
 typedef enum { DGS_I32 = 0, DGS_I64 = 1 } dgs_itype_t;
 
@@ -116,7 +117,9 @@ int dgs_loc_table_unpack(const void *table, int64_t capacity, int itype, void *k
  * replaces GetFeaturesCUDA / _IndexKernel (src/feature/cuda/feature_ops.cu:140-210) and
  * GetFeaturesP2PCacheCUDA / _IndexP2PCacheKernel (feature_ops.cu:38-138).
  * Rows are raw bytes (row_bytes = stride * element size), so any dtype works.
- * algo: 0 = auto, 1 = vectorised LDG/STG gather, 2 = TMA bulk (cp.async.bulk) staged gather. */
+ * algo: 0 = auto, 1 = CTA-tile vectorised LDG/STG gather, 2 = TMA bulk (cp.async.bulk) staged
+ * gather, 3 = warp-autonomous vectorised gather (what auto picks for 16-byte aligned rows);
+ * 4-6 = tuning variants of 3 (tools/extract_probe.py). */
 int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids, int64_t n,
                      void *out, int algo, void *stream);
 /* cached gather: row i comes from peer shard feat[dev][idx] when nids[i] hits the location
@@ -213,11 +216,17 @@ int dgs_debug_ares_keys(const float *weights, int64_t deg, uint64_t rng_key, uin
  * Capacities: cap_edges[l] >= ub_l * k_l, cap_frontier[l] >= ub_l * (1 + k_l) with
  * ub_0 = num_seeds, ub_{l+1} = ub_l * (1 + k_l).
  * ws: dgs_sample_blocks_ws_bytes(...) bytes, initialised ONCE with dgs_sample_blocks_ws_init for
- * the same (itype, num_seeds, num_layers, fan_out, num_nodes = g->num_nodes); epoch = number of dgs_sample_blocks calls
- * already made on this workspace since its init (0, 1, 2, ...): the relabel table a call leaves
- * dirty is wiped by the first kernel of the next call, which needs to know which of the two
- * alternating tables that is.  One cooperative launch per batch (or 3 kernels per hop when the
- * fan-out is too large for the tile kernels), no memset, no trailing clean-up launch.
+ * the same (itype, num_seeds, num_layers, fan_out, num_nodes = g->num_nodes) - the library
+ * remembers what a workspace was initialised for and REFUSES a call that does not match (a
+ * different layout would read the relabel tables at the wrong offsets); with direct-addressed
+ * tables (num_nodes known) fewer seeds than at init are accepted.  One workspace serves one stream
+ * at a time.  epoch = number of dgs_sample_blocks calls already made on this workspace since its
+ * init (0, 1, 2, ...): only the hashed-table path (num_nodes = 0) uses it - the relabel table a call
+ * leaves dirty there is wiped by the first kernel of the next call, which needs to know which of the
+ * two alternating tables that is; the direct-table path tags its entries with an epoch it keeps
+ * itself and ignores the argument.
+ * One cooperative launch per batch (or 3 kernels per hop when the fan-out is 0 or too large for
+ * the tile kernels), no memset, no trailing clean-up launch.
  * counts_host (optional, pinned host memory, 2 L int64): when non-NULL the call returns once the
  * counts have arrived there - the single host round trip of a batch.  If the memory is mapped
  * into the device's address space (cudaHostAlloc / cudaHostRegister under UVA) the cooperative
@@ -247,6 +256,34 @@ int dgs_sample_blocks_enqueue(const dgs_graph_t *g, const void *seeds, int64_t n
                               int64_t *counts_host, void *stream);
 int dgs_sample_blocks_wait(int64_t *counts_host, const int64_t *counts_dev, int num_layers,
                            void *stream);
+
+/* B independent mini-batches of the same shape in ONE cooperative launch (extension):
+ * a batch of ~1000 seeds cannot fill 148 SMs, so the hops of all B batches walk through the kernel's
+ * phases together and share every grid barrier.  Bit-identical to B dgs_sample_blocks calls with
+ * rng_seeds[b].  Batch b reads seeds + b * seeds_stride_bytes and writes out_*[l] + b *
+ * out_stride_bytes (out_* / cap_* describe batch 0); counts_dev / counts_host hold [B][2 L] int64.
+ * Needs direct-addressed relabel tables (g->num_nodes known), fan-outs in [1, ~120] and <= 8 hops:
+ * dgs_sample_blocks_multi_ws_bytes returns -1 otherwise (use the single-batch entry).  ws: sized
+ * and initialised ONCE for (itype, num_batches, num_seeds, num_layers, fan_out, num_nodes); later
+ * calls may pass fewer batches / fewer seeds per batch.  The relabel table of a batch (8 bytes per
+ * node) is never wiped: entries carry an 8-bit epoch tag that the library advances per hop (and
+ * clears the table every 255 hops), so a workspace must be used by one stream at a time and the
+ * items of a hop (seeds + padded slots) must stay below 2^24 (else -1 from ..._ws_bytes).
+ * wait != 0: return once the sizes are in counts_host (pinned, required); wait == 0: enqueue only -
+ * when counts_host is mapped pinned memory the kernel delivers the sizes there and
+ * dgs_sample_blocks_wait(counts_host, counts_dev, num_layers * num_batches, stream) collects them. */
+int64_t dgs_sample_blocks_multi_ws_bytes(int itype, int num_batches, int64_t num_seeds,
+                                         int num_layers, const int64_t *fan_out, int64_t num_nodes);
+int dgs_sample_blocks_multi_ws_init(void *ws, int64_t ws_bytes, int itype, int num_batches,
+                                    int64_t num_seeds, int num_layers, const int64_t *fan_out,
+                                    int64_t num_nodes, void *stream);
+int dgs_sample_blocks_multi(const dgs_graph_t *g, int num_batches, const void *seeds,
+                            int64_t seeds_stride_bytes, int64_t num_seeds, int num_layers,
+                            const int64_t *fan_out, int replace, const uint64_t *rng_seeds,
+                            void *const *out_frontier, void *const *out_row, void *const *out_col,
+                            int64_t out_stride_bytes, const int64_t *cap_edges,
+                            const int64_t *cap_frontier, int64_t *counts_dev, void *ws,
+                            int64_t ws_bytes, int64_t *counts_host, int wait, void *stream);
 
 /* ------------------------------------------------------------------ relabel
  * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):

@@ -245,6 +245,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arms of bench.py ask for all host cores
+ * explicitly (n <= 0: the number of processors). */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+  (void)n;
+#endif
+}
+
 /* DGL-semantics sample_neighbors (COO, seed-major).  probs == NULL: uniform.  replace = 0.
  * Two passes over the seeds: counts -> exclusive offsets -> fill.  Returns nnz; out arrays need
  * n * k entries (k >= 0) or the exact nnz when k < 0. */

@@ -54,6 +54,18 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n=0):
+    """OpenMP threads of the CPU baseline (n <= 0: every host core this process may use).  torchrun
+    sets OMP_NUM_THREADS=1 for its workers, so bench.py's CPU arms call this first."""
+    if n <= 0:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def index_select(table, nids):
     """feature_ops.cu:140-210 - out[i] = table[nids[i]] (bytes are copied, any dtype)."""
     table = np.ascontiguousarray(table)

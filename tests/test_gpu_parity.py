@@ -805,6 +805,119 @@ def test_fused_blocks_direct_equals_hashed_tables(dgs, cuda, idt, bias):
             assert all(torch.equal(x, y) for u, v in zip(a, b) for x, y in zip(u, v))
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("bias,replace", [(False, False), (True, False), (False, True), (True, True)])
+def test_sample_many_equals_single_calls(dgs, cuda, idt, bias, replace):
+    """B mini-batches in ONE cooperative launch (dgs_sample_blocks_multi) must be bit-identical to B
+    single-batch calls with the same RNG seeds - every hop, every tensor - for B = 1, 3, 8, on a graph
+    with hub rows, duplicate seeds in hop 0, batch sizes that are not tile multiples, and repeated
+    launches on the same workspace (its relabel tables must come back clean)."""
+    N = 20000
+    indptr, indices, probs = dgs_synth.make_csr(N, 900000, seed=71, weights=bias, id_dtype=idt)
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda), probs.to(cuda) if bias else None)
+    g = torch.Generator().manual_seed(7)
+    fan = [15, 10, 5]
+    for B, S in ((1, 1024), (3, 333), (8, 512), (8, 512)):
+        seeds = torch.randint(0, N, (B, S), generator=g).to(idt).to(cuda)     # duplicates inside a batch
+        rng = [1000 + 17 * b for b in range(B)]
+        many = smp.sample_many(seeds, fan, replace, rng)
+        assert len(many) == B
+        for b in range(B):
+            one = smp._CAPI_sample_node_classifiction(seeds[b].clone(), fan, replace, rng_seed=rng[b])
+            assert len(one) == len(many[b]) == 3
+            for x, y in zip(many[b], one):
+                for u, v in zip(x, y):
+                    assert torch.equal(u, v)
+    # a second fan-out shape (two hops, k > 16: Floyd in shared memory) and the deterministic path
+    maxdeg_fan = [40, 20]
+    seeds = torch.randperm(N, generator=g)[:4 * 200].reshape(4, 200).to(idt).to(cuda)
+    many = smp.sample_many(seeds, maxdeg_fan, replace, [5, 6, 7, 8])
+    for b in range(4):
+        one = smp._CAPI_sample_node_classifiction(seeds[b].clone(), maxdeg_fan, replace, rng_seed=5 + b)
+        assert all(torch.equal(u, v) for x, y in zip(many[b], one) for u, v in zip(x, y))
+
+
+def test_sample_many_copy_path_matches_oracle(dgs, cuda):
+    """All-neighbour fan-outs through the multi-batch kernel against the oracle's layer loop."""
+    N = 1500
+    indptr, indices, _ = dgs_synth.make_csr(N, 9000, seed=11, classes=5)
+    maxdeg = int((indptr[1:] - indptr[:-1]).max())
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    g = torch.Generator().manual_seed(3)
+    seeds = torch.randint(0, N, (5, 40), generator=g)
+    many = smp.sample_many(seeds.to(cuda), [maxdeg, maxdeg], False, [1, 2, 3, 4, 5])
+    for b in range(5):
+        exp = oracle.sample_blocks_all_neighbors(t2n(seeds[b]), t2n(indptr), t2n(indices), 2)
+        for a, e in zip(many[b], exp):
+            for x, z in zip(a, e):
+                assert np.array_equal(t2n(x), z)
+
+
+def test_sample_blocks_workspace_is_checked(dgs, cuda):
+    """A workspace remembers what it was initialised for: fewer seeds than at init are fine with
+    direct tables (same result as a fresh call), anything else is refused instead of silently
+    reading the relabel tables at the wrong offsets; so is a pointer that was never initialised."""
+    import ctypes as C
+    from dgs import _lib
+    from dgs._util import stream
+    l = _lib.lib()
+    N = 8000
+    indptr, indices, _ = dgs_synth.make_csr(N, 200000, seed=5)
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    pipe = smp._pipe
+    fan = [10, 5]
+    big = pipe._plan(512, fan)
+    seeds = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:300].to(cuda)
+
+    def call(pl, ws, S, fo):
+        arena = torch.empty(pl["total"] + pl["count_slots"], dtype=torch.int64, device=cuda)
+        base = arena.data_ptr()
+        for li, (of, orow, ocol) in enumerate(pl["offs"]):
+            pl["a_fr"][li], pl["a_row"][li], pl["a_col"][li] = base + of * 8, base + orow * 8, base + ocol * 8
+        rc = l.dgs_sample_blocks(C.byref(pipe._graph), seeds.data_ptr(), S, len(fo), _lib.i64_array(fo), 0,
+                                 C.c_uint64(9), pl["a_fr"], pl["a_row"], pl["a_col"], pl["cap_edges"],
+                                 pl["cap_front"], base + pl["total"] * 8, ws.data_ptr(), ws.numel(), 0,
+                                 pl["counts_ptr"], stream())
+        return rc, arena
+    rc, arena = call(big, big["ws"], 300, fan)
+    assert rc == 0
+    ref = smp._CAPI_sample_node_classifiction(seeds, fan, False, rng_seed=9)
+    counts = big["counts_np"].tolist()
+    assert counts == [ref[0][2].numel(), ref[0][1].numel(), ref[1][2].numel(), ref[1][1].numel()]
+    of, orow, ocol = big["offs"][1]
+    assert torch.equal(arena[of:of + counts[3]], ref[1][1]) and torch.equal(arena[ocol:ocol + counts[2]], ref[1][3])
+    rc, _ = call(big, big["ws"], 300, [10, 6])                    # another fan-out
+    assert rc != 0 and b"another configuration" in l.dgs_last_error()
+    bigger = pipe._plan(600, fan)
+    rc, _ = call(bigger, big["ws"], 600, fan)                     # more seeds than at init
+    assert rc != 0 and b"another configuration" in l.dgs_last_error()
+    stray = torch.empty(big["ws"].numel(), dtype=torch.uint8, device=cuda)
+    rc, _ = call(big, stray, 300, fan)
+    assert rc != 0 and b"never initialised" in l.dgs_last_error()
+
+
+def test_batch_loader_load_many(dgs, cuda):
+    """BatchLoader.load_many (B batches, one sampling launch) == B x load() with the same seeds."""
+    N, D = 9000, 100
+    indptr, indices, _ = dgs_synth.make_csr(N, 200000, seed=45, classes=8)
+    feat = dgs_synth.feature_rows(torch.arange(N), D)
+    labels = (torch.arange(N) % 47).to(cuda)
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    for src in (feat.to(cuda), dgs.classes.P2PCacheFeatureServer(feat.pin_memory(), torch.arange(N), 0)):
+        loader = dgs.classes.BatchLoader(smp, src, labels)
+        g = torch.Generator().manual_seed(8)
+        for it in range(3):
+            seeds = torch.randperm(N, generator=g)[:6 * 128].reshape(6, 128)
+            rng = [it * 10 + b for b in range(6)]
+            res = loader.load_many(seeds.pin_memory() if it % 2 else seeds.to(cuda), [10, 5], False, rng)
+            assert len(res) == 6
+            for b, (blocks, x, y) in enumerate(res):
+                rb, rx, ry = loader.load(seeds[b].to(cuda), [10, 5], False, rng_seed=rng[b])
+                assert all(torch.equal(u, v) for p_, q_ in zip(blocks, rb) for u, v in zip(p_, q_))
+                assert torch.equal(x, rx) and torch.equal(y, ry)
+                assert torch.equal(x.cpu(), feat[blocks[-1][1].cpu()])
+
+
 @pytest.mark.parametrize("bias", [False, True])
 def test_huge_num_picks_uses_output_scratch(dgs, cuda, bias):
     """num_picks far beyond what shared memory holds (the reference asserts num_picks <= 32 for the
