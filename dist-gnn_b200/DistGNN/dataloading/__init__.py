@@ -6,5 +6,6 @@
 from .blocks import NID, Block, build_blocks
 from .dataloader import SeedGenerator
 from .load_dataset import load_dataset
+from . import dataset_preprocess
 
-__all__ = ["NID", "Block", "build_blocks", "SeedGenerator", "load_dataset"]
+__all__ = ["NID", "Block", "build_blocks", "SeedGenerator", "load_dataset", "dataset_preprocess"]

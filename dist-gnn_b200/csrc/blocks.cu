@@ -1400,8 +1400,11 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
 // kernel per phase gets its own register budget - the rank and emit phases run at 4 CTAs per SM
 // instead of the 2 the pick phase's registers allow the fused kernel; the kernel boundaries
 // (~3 us each) are shared by the B batches.
+#ifndef DGS_MB_PICK_CTAS
+#define DGS_MB_PICK_CTAS 3  // measured at B = 8: 37.4 (2) / 36.3 (3) / 37.0 (4) us per batch
+#endif
 template <typename IdT, typename ET, int MODE>
-__global__ void __launch_bounds__(kBkThreads, 2)
+__global__ void __launch_bounds__(kBkThreads, DGS_MB_PICK_CTAS)
 mb_pick_kernel(GraphSrc g, BlocksWs ws0, MbArgs a, int l) {
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
@@ -1614,7 +1617,7 @@ static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t se
     auto kp = mb_pick_kernel<IdT, ET, M>;                                                            \
     if (sm_pick > 32 * 1024)                                                                         \
       DGS_CUDA_OK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pick)); \
-    kp<<<sms * 2, kBkThreads, sm_pick, st>>>(src, ws, a, l);                                         \
+    kp<<<sms * DGS_MB_PICK_CTAS, kBkThreads, sm_pick, st>>>(src, ws, a, l);                                         \
   } while (0)
       switch (mode) {
         case kUniform: DGS_MBP(kUniform); break;

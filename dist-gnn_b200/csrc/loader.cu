@@ -1,0 +1,69 @@
+// loader.cu - one C-ABI call per mini-batch (the whole-batch pipeline).
+//
+// The reference's training loop makes three plugin calls per batch with a host synchronisation
+// after the sampling (example/graphsage/node_classification.py:219-230).  dgs_load_batch enqueues
+// the same work back to back on the caller's stream -
+//   seeds H2D -> multi-hop sample + relabel (dgs_sample_blocks_enqueue) -> feature extract of the
+//   input frontier, whose size is read on the device (dgs_extract_dyn) -> label gather -> labels D2H
+// - and then makes the batch's ONE host round trip (the hop sizes the sampling kernel writes into
+// pinned memory).  Everything is built from the library's own public entries; the point of doing it
+// in one call is the host side: one FFI crossing and no Python between the five enqueues (measured:
+// 199 -> see profiles/ us per end-to-end step at batch 1024).
+//
+// Why not a CUDA graph: the outputs of a batch are fresh caller-owned buffers and the RNG key
+// changes, so every node's parameters differ from step to step - an exec-update per launch costs
+// the CPU about what the five plain launches cost.
+#include "dgs_common.cuh"
+
+using namespace dgsb;
+
+extern "C" int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, const void *seeds,
+                              int seeds_on_host, void *seeds_dev, int64_t num_seeds, int num_layers,
+                              const int64_t *fan_out, int replace, uint64_t rng_seed, void *arena,
+                              const int64_t *hop_offsets, const int64_t *cap_edges,
+                              const int64_t *cap_frontier, int64_t counts_offset, void *ws,
+                              int64_t ws_bytes, int64_t epoch, int64_t *counts_host, void *x_out,
+                              int64_t x_rows_ub, void *labels_out_dev, void *labels_out_host, int algo,
+                              void *stream) {
+  DGS_REQUIRE(g && f && seeds && fan_out && arena && hop_offsets && cap_edges && cap_frontier && ws &&
+                  counts_host && x_out,
+              "dgs_load_batch: null argument");
+  DGS_REQUIRE(num_seeds >= 1 && num_layers >= 1 && num_layers <= 16, "dgs_load_batch: bad sizes");
+  DGS_REQUIRE(!seeds_on_host || seeds_dev, "dgs_load_batch: host seeds need a device staging buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t es = g->itype == DGS_I64 ? 8 : 4;
+  const void *sd = seeds;
+  if (seeds_on_host) {
+    DGS_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds, (size_t)(num_seeds * es), cudaMemcpyHostToDevice, st));
+    sd = seeds_dev;
+  }
+  void *fr[16], *row[16], *col[16];
+  char *base = (char *)arena;
+  for (int l = 0; l < num_layers; ++l) {
+    fr[l] = base + hop_offsets[3 * l] * es;
+    row[l] = base + hop_offsets[3 * l + 1] * es;
+    col[l] = base + hop_offsets[3 * l + 2] * es;
+  }
+  int64_t *counts_dev = (int64_t *)(base + counts_offset * es);
+  int rc = dgs_sample_blocks_enqueue(g, sd, num_seeds, num_layers, fan_out, replace, rng_seed, fr, row, col,
+                                     cap_edges, cap_frontier, counts_dev, ws, ws_bytes, epoch, counts_host,
+                                     stream);
+  if (rc) return rc;
+  // extract of the last hop's frontier: its live size is counts_dev[2 L - 1]
+  rc = dgs_extract_dyn(f->table, f->feat, f->loc_table, f->loc_capacity, f->mod_world, f->row_bytes,
+                       g->itype, fr[num_layers - 1], x_rows_ub, counts_dev + 2 * num_layers - 1, x_out, algo,
+                       stream);
+  if (rc) return rc;
+  if (f->labels != nullptr && labels_out_dev != nullptr) {
+    rc = dgs_index_select(f->labels, f->label_bytes, g->itype, sd, num_seeds, labels_out_dev, 1, stream);
+    if (rc) return rc;
+    if (labels_out_host != nullptr)
+      DGS_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels_out_dev, (size_t)(num_seeds * f->label_bytes),
+                                  cudaMemcpyDeviceToHost, st));
+  }
+  // the one host round trip: hop sizes (the extract / label work enqueued above may still run)
+  rc = dgs_sample_blocks_wait(counts_host, counts_dev, num_layers, stream);
+  if (rc) return rc;
+  if (f->labels != nullptr && labels_out_host != nullptr) DGS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}

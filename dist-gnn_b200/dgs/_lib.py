@@ -34,6 +34,20 @@ class Graph(C.Structure):
     ]
 
 
+class Features(C.Structure):
+    """dgs_features_t"""
+    _fields_ = [
+        ("table", c_vp),
+        ("feat", c_vp),
+        ("loc_table", c_vp),
+        ("loc_capacity", c_i64),
+        ("mod_world", C.c_int32),
+        ("row_bytes", c_i64),
+        ("labels", c_vp),
+        ("label_bytes", c_i64),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/dgs_b200.h declares
 SIGNATURES = {
     "dgs_abi_version": (C.c_int, []),
@@ -94,6 +108,9 @@ SIGNATURES = {
     "dgs_sample_blocks_multi": (C.c_int, [C.POINTER(Graph), C.c_int, c_vp, c_i64, c_i64, C.c_int, c_i64p,
                                           C.c_int, C.POINTER(C.c_uint64), c_vpp, c_vpp, c_vpp, c_i64,
                                           c_i64p, c_i64p, c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp]),
+    "dgs_load_batch": (C.c_int, [C.POINTER(Graph), C.POINTER(Features), c_vp, C.c_int, c_vp, c_i64, C.c_int,
+                                 c_i64p, C.c_int, C.c_uint64, c_vp, c_i64p, c_i64p, c_i64p, c_i64, c_vp,
+                                 c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, C.c_int, c_vp]),
     "dgs_relabel_table_capacity": (c_i64, [c_i64]),
     "dgs_relabel_table_bytes": (c_i64, [c_i64]),
     "dgs_relabel_ws_bytes": (c_i64, [c_i64]),

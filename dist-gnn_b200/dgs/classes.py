@@ -278,6 +278,7 @@ class _BlockPipeline:
                     off += u + 3 * n
                 counts_host = torch.empty(2 * L, dtype=torch.int64).pin_memory()
                 pl.update(ws=ws, ws_bytes=int(nbytes), fo=fo, epoch=0, es=es, offs=offs,
+                          hop_offs=_lib.i64_array([o for t in offs for o in t]),
                           cap_edges=_lib.i64_array(nnz_ubs),
                           cap_front=_lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
                           a_fr=(C.c_void_p * L)(), a_row=(C.c_void_p * L)(),
@@ -845,6 +846,28 @@ class BatchLoader:
         self._labels = labels
         if labels is not None:
             check_device_readable(labels, "labels")
+            contiguous(labels, "labels")
+        # dgs_features_t of the one-call native loader (dgs_load_batch)
+        f = _lib.Features()
+        if self._fs is None:
+            f.table = ptr(self._table)
+        elif self._fs._mod_world < 0:     # full replica: the local shard is a plain table
+            f.table = self._fs.gpu_features_._local_ptr
+        else:
+            fs = self._fs
+            f.table = fs._host_ptr
+            f.feat = fs.gpu_features_._handle
+            f.loc_table = ptr(fs._table) if fs._table is not None else None
+            f.loc_capacity = fs._cap
+            f.mod_world = max(fs._mod_world, 0)
+        f.row_bytes = self._row_bytes
+        if labels is not None:
+            lstride = 1
+            for d in labels.shape[1:]:
+                lstride *= d
+            f.labels = ptr(labels)
+            f.label_bytes = lstride * labels.element_size()
+        self._feat_struct = f
 
     def _extract_dyn(self, it, front_ptr, n_ub, nf_dev, out_ptr, algo):
         """Enqueue the gather of a frontier whose size is still on the device (dgs_extract_dyn)."""
@@ -926,40 +949,49 @@ class BatchLoader:
 
     def load(self, seeds, fan_out, replace=False, rng_seed=None, algo=0, labels_out=None):
         """-> (blocks, features of blocks[-1][1], labels of seeds or None).  `labels_out` (pinned host
-        tensor) additionally receives the labels inside the same host round trip."""
+        tensor) additionally receives the labels inside the same host round trip.  One native call
+        (dgs_load_batch) enqueues seeds H2D -> sample -> extract -> labels (-> D2H) and waits for the
+        hop sizes."""
         l = lib()
         fan_out = [int(k) for k in fan_out]
         L = len(fan_out)
         if L == 0 or any(k < 0 for k in fan_out):
             raise RuntimeError("BatchLoader needs fan-outs >= 0 (use the plugin calls for -1)")
         with _on_device(self._device):
-            if not seeds.is_cuda:
-                seeds = seeds.to(self._device, non_blocking=True)     # pinned host -> device
+            on_host = not seeds.is_cuda
+            if on_host and not seeds.is_pinned():
+                seeds = seeds.to(self._device)
+                on_host = False
             seeds = seeds.contiguous()
+            S = seeds.numel()
             if rng_seed is None:
                 rng_seed = l.dgs_randn_uint64()
-            pl = self._pipe._plan(seeds.numel(), fan_out)
-            if pl["ws"] is None or seeds.numel() == 0:
+            pl = self._pipe._plan(S, fan_out)
+            if pl["ws"] is None or S == 0:
                 raise RuntimeError("BatchLoader: batch too large for the fused path")
-            arena = self._pipe.enqueue_only(seeds, fan_out, replace, rng_seed, deliver_counts=True)
-            es, base = pl["es"], arena.data_ptr()
-            counts_ptr = base + pl["total"] * es
+            if seeds.dtype != self._pipe._id_dtype:
+                raise RuntimeError("seeds must have the id type of indices")
+            arena = torch.empty(pl["total"] + pl["count_slots"], dtype=seeds.dtype, device=self._device)
+            seeds_dev = torch.empty(S, dtype=seeds.dtype, device=self._device) if on_host else seeds
             n_max = pl["ubs"][-1] + pl["nnz_ubs"][-1]
             # output rows: the worst case the first time, then 1.25x the largest frontier seen for
             # this (batch, fan-out) - a batch that overflows is re-extracted exactly (rare)
             seen = pl.get("front_seen", 0)
             n_ub = n_max if seen == 0 else min(n_max, seen + seen // 4 + 1024)
-            front_ptr = base + pl["offs"][-1][0] * es
             x = torch.empty((n_ub,) + self._tail, dtype=self._dtype, device=self._device)
-            it = ID_DTYPES[seeds.dtype]
-            nf_dev = counts_ptr + 8 * (2 * L - 1)
-            self._extract_dyn(it, front_ptr, n_ub, nf_dev, ptr(x), algo)
-            y = ops._CAPI_cuda_index_select(self._labels, seeds) if self._labels is not None else None
-            if labels_out is not None and y is not None:
-                labels_out.copy_(y, non_blocking=True)
-            # the one host round trip: the sampling kernel has written the hop sizes into pinned
-            # memory; the extract / label kernels enqueued above may still be running
-            self._pipe.wait_counts(pl, arena)
+            y = None
+            if self._labels is not None:
+                y = torch.empty((S,) + tuple(self._labels.shape[1:]), dtype=self._labels.dtype,
+                                device=self._device)
+            check(l.dgs_load_batch(
+                C.byref(self._pipe._graph), C.byref(self._feat_struct), seeds.data_ptr(), int(on_host),
+                seeds_dev.data_ptr(), S, L, pl["fo"], int(bool(replace)), C.c_uint64(rng_seed),
+                arena.data_ptr(), pl["hop_offs"], pl["cap_edges"], pl["cap_front"], pl["total"],
+                pl["ws"].data_ptr(), pl["ws_bytes"], pl["epoch"], pl["counts_ptr"], x.data_ptr(), n_ub,
+                ptr(y) if y is not None else None,
+                labels_out.data_ptr() if (labels_out is not None and y is not None) else None,
+                int(algo), stream()), "load_batch")
+            pl["epoch"] += 1
             counts = pl["counts_np"].tolist()
             sizes = []
             for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
@@ -975,12 +1007,9 @@ class BatchLoader:
             else:
                 x = x[:nf]
             blocks = []
-            cur = seeds
+            cur = seeds_dev
             for li in range(L):
                 frontier = parts[6 * li]
                 blocks.append((cur, frontier, parts[6 * li + 2], parts[6 * li + 4]))
                 cur = frontier
-            if labels_out is not None and y is not None:
-                torch.cuda.current_stream().synchronize()    # labels_out is read by the host
         return blocks, x, y
-

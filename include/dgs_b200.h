@@ -285,6 +285,37 @@ int dgs_sample_blocks_multi(const dgs_graph_t *g, int num_batches, const void *s
                             const int64_t *cap_frontier, int64_t *counts_dev, void *ws,
                             int64_t ws_bytes, int64_t *counts_host, int wait, void *stream);
 
+/* ------------------------------------------------------------------ whole-batch loader
+ * One call per mini-batch = the caller loop of example/graphsage/node_classification.py:219-230
+ * (sampler._CAPI_sample_node_classifiction, feature_server._CAPI_get_feature, label index_select)
+ * enqueued back to back with ONE host round trip: seeds H2D (when seeds_on_host: `seeds` is pinned
+ * host memory, seeds_dev a device staging buffer of num_seeds ids) -> dgs_sample_blocks_enqueue ->
+ * dgs_extract_dyn of the input frontier (size read on the device; x_out holds x_rows_ub rows) ->
+ * label gather into labels_out_dev (+ D2H into pinned labels_out_host).  Outputs: `arena` (ids) holds
+ * hop l's frontier / row / col at hop_offsets[3 l .. 3 l + 2] (elements) and the 2 L int64 hop sizes
+ * at counts_offset (elements); the sizes are also in counts_host (pinned) when the call returns.
+ * With labels_out_host the call returns after the stream has drained, else right after the sizes
+ * arrived (extract / label kernels may still be running, ordered on `stream`).  If the frontier
+ * turned out larger than x_rows_ub (the caller's bound) only x_rows_ub rows were gathered. */
+typedef struct {
+  const void *table;            /* plain table (device / pinned host), or the pinned-host fallback of a
+                                   cached source (may be NULL when every row is cached) */
+  const dgs_p2p_server_t *feat; /* cached source: feature shards (NULL = plain table) */
+  const void *loc_table;        /* location table of the cached source (NULL with mod_world != 0) */
+  int64_t loc_capacity;
+  int32_t mod_world;            /* > 0: modulo-sharded, 0: location table */
+  int64_t row_bytes;
+  const void *labels;           /* label table indexed by node id (device / pinned host) or NULL */
+  int64_t label_bytes;          /* bytes per label row */
+} dgs_features_t;
+int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, const void *seeds, int seeds_on_host,
+                   void *seeds_dev, int64_t num_seeds, int num_layers, const int64_t *fan_out,
+                   int replace, uint64_t rng_seed, void *arena, const int64_t *hop_offsets,
+                   const int64_t *cap_edges, const int64_t *cap_frontier, int64_t counts_offset,
+                   void *ws, int64_t ws_bytes, int64_t epoch, int64_t *counts_host, void *x_out,
+                   int64_t x_rows_ub, void *labels_out_dev, void *labels_out_host, int algo,
+                   void *stream);
+
 /* ------------------------------------------------------------------ relabel
  * replaces TensorRelabelCUDA (src/sampling/cuda/tensor_relabel.cu:182-205):
  * unique = first-occurrence-order unique of the concatenation of the mapping parts, every id of
