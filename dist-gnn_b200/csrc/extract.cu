@@ -27,6 +27,7 @@ struct RowSource {
   uint64_t cap_mask;
   PtrTable shards;
   int mod_world;  // > 0: row n lives in shard n % mod_world at slot n / mod_world (no table)
+  int peers;      // shards of other GPUs are among the sources (NVLink peer loads)
   const long long *n_dev;  // optional live row count on the device (the kernel's n is then a bound)
 };
 
@@ -184,6 +185,58 @@ gather_rows_warp_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// algo 7: row-aligned warp gather.  Same warp-autonomous structure as algo 3, but a load
+// instruction never straddles two rows: the warp is cut into groups of G = 2^ceil(log2(vpr)) lanes
+// (32 for 400- and 512-byte rows) and each group reads ONE row per instruction, lane c < vpr taking
+// vector c.  Lanes >= vpr idle (25 of 32 active on 400-byte rows), but every 128-byte line of a
+// source row is requested exactly once - in the flat scheme the line that straddles an instruction
+// boundary is requested twice (ncu on NVLink peer rows: 4.66 read requests per 400-byte row, 4 is
+// the minimum), and the request rate is what bounds peer reads of rows that are not line multiples.
+template <typename IdT, int U>
+__global__ void __launch_bounds__(kWarpGatherWarps * 32)
+gather_rows_aligned_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64_t row_bytes,
+                           uint32_t vpr, int gshift, char *__restrict__ out) {
+  __shared__ const char *s_src[kWarpGatherWarps][32];
+  if (src.n_dev != nullptr) n = min(n, (int64_t)*src.n_dev);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = 1 << gshift;               // lanes per row
+  const int rpi = 32 >> gshift;            // rows per instruction
+  const int sub = lane >> gshift;          // which row of the instruction this lane works on
+  const uint32_t c0 = (uint32_t)(lane & (G - 1));
+  const int64_t groups = (n + 31) >> 5;
+  const int64_t gstride = (int64_t)gridDim.x * kWarpGatherWarps;
+  int64_t g = (int64_t)blockIdx.x * kWarpGatherWarps + warp;
+  IdT nid = 0;
+  if (g < groups && g * 32 + lane < n) nid = nids[g * 32 + lane];
+  for (; g < groups; g += gstride) {
+    const int64_t row0 = g << 5;
+    const int rows = (int)min((int64_t)32, n - row0);
+    __syncwarp();
+    if (lane < rows) s_src[warp][lane] = resolve_row<IdT>(src, nid, row_bytes);
+    const int64_t g2 = g + gstride;
+    if (g2 < groups && g2 * 32 + lane < n) nid = nids[g2 * 32 + lane];
+    __syncwarp();
+    char *otile = out + row0 * row_bytes;
+    for (uint32_t cb = 0; cb < vpr; cb += (uint32_t)G) {      // one pass unless a row exceeds 512 bytes
+      const uint32_t c = cb + c0;
+      for (int r0 = 0; r0 < rows; r0 += rpi * U) {
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = r0 + u * rpi + sub;
+          if (r < rows && c < vpr) v[u] = ld_nc_v4(reinterpret_cast<const int4 *>(s_src[warp][r]) + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = r0 + u * rpi + sub;
+          if (r < rows && c < vpr) st_na_v4(reinterpret_cast<int4 *>(otile + (int64_t)r * row_bytes) + c, v[u]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // algo 2: TMA bulk-copy ring (row_bytes % 16 == 0, 16-byte aligned tables).
 constexpr int kTmaRows = 32;      // rows per stage = one per lane
 constexpr int kTmaPrefetch = 3;   // tiles of row loads in flight per warp
@@ -333,6 +386,11 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
   // default (measured on B200, tools/extract_probe.py): launches of >= 128 MB of rows go to the
   // warp-autonomous gather (0.82 vs 0.80 of peak at 1 M x 400 B, 0.94 vs 0.90 at 1 M x 512 B),
   // mini-batch-sized ones to the CTA-tile kernel (0.71 both at 192 k x 400 B, 0.82 vs 0.81 at 512 B)
+  // Peer shards with rows that are not multiples of the 128-byte line: the row-aligned variant
+  // (one read request per line; 595 vs 524 GB/s of payload over NVLink at 400-byte rows).
+  if (algo == 0 && src.peers && all_aligned16 && row_bytes % 16 == 0 && row_bytes % 128 != 0 &&
+      row_bytes >= 64)
+    algo = 7;
   if (algo == 0)
     algo = (all_aligned16 && row_bytes % 16 == 0 && row_bytes >= 64 && row_bytes / 16 * 32 < 65536 &&
             n * row_bytes >= (128ll << 20)) ? 3 : 1;
@@ -345,6 +403,18 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
     if (per_sm > 16) per_sm = 16;
     int grid = grid_for(n, kTmaRows, per_sm);
     kern<<<grid, 32, smem, st>>>(src, nids, n, row_bytes, out);
+    DGS_LAUNCH_CHECK();
+    return 0;
+  }
+  if (algo == 7) {
+    DGS_REQUIRE(all_aligned16 && row_bytes % 16 == 0, "extract: algo 7 needs 16-byte aligned tables and "
+                "row_bytes %% 16 == 0 (row_bytes=%lld)", (long long)row_bytes);
+    const uint32_t vpr = (uint32_t)(row_bytes / 16);
+    int gshift = 0;
+    while ((1u << gshift) < vpr && gshift < 5) ++gshift;
+    const int grid = grid_for(n, 32 * kWarpGatherWarps, 8);
+    gather_rows_aligned_kernel<IdT, 8><<<grid, kWarpGatherWarps * 32, 0, st>>>(src, nids, n, row_bytes, vpr,
+                                                                            gshift, out);
     DGS_LAUNCH_CHECK();
     return 0;
   }
@@ -435,6 +505,7 @@ extern "C" int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_ta
   src.table = (const char *)host_table;
   src.loc = (const LocSlot *)loc_table;
   src.cap_mask = (uint64_t)capacity - 1;
+  src.peers = feat->world > 1;
   bool al = aligned16(out) && (host_table == nullptr || aligned16(host_table));
   for (int d = 0; d < feat->world; ++d) {
     src.shards.p[d] = feat->ptrs[d];
@@ -458,6 +529,7 @@ extern "C" int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_byt
   RowSource src;
   memset(&src, 0, sizeof(src));
   src.mod_world = feat->world;
+  src.peers = feat->world > 1;
   bool al = aligned16(out);
   for (int d = 0; d < feat->world; ++d) {
     src.shards.p[d] = feat->ptrs[d];
@@ -487,6 +559,7 @@ extern "C" int dgs_extract_dyn(const void *table, const dgs_p2p_server_t *feat, 
   src.n_dev = (const long long *)n_dev;
   bool al = aligned16(out) && (table == nullptr || aligned16(table));
   if (feat != nullptr) {
+    src.peers = feat->world > 1;
     for (int d = 0; d < feat->world; ++d) {
       src.shards.p[d] = feat->ptrs[d];
       al = al && aligned16(feat->ptrs[d]);

@@ -118,8 +118,9 @@ int dgs_loc_table_unpack(const void *table, int64_t capacity, int itype, void *k
  * GetFeaturesP2PCacheCUDA / _IndexP2PCacheKernel (feature_ops.cu:38-138).
  * Rows are raw bytes (row_bytes = stride * element size), so any dtype works.
  * algo: 0 = auto, 1 = CTA-tile vectorised LDG/STG gather, 2 = TMA bulk (cp.async.bulk) staged
- * gather, 3 = warp-autonomous vectorised gather (what auto picks for 16-byte aligned rows);
- * 4-6 = tuning variants of 3 (tools/extract_probe.py). */
+ * gather, 3 = warp-autonomous vectorised gather (auto: launches of >= 128 MB), 7 = row-aligned
+ * warp gather (auto: peer shards whose rows are not multiples of 128 bytes); 4-6 = tuning variants
+ * of 3 (tools/extract_probe.py). */
 int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids, int64_t n,
                      void *out, int algo, void *stream);
 /* cached gather: row i comes from peer shard feat[dev][idx] when nids[i] hits the location

@@ -24,10 +24,10 @@ def small_graph(N=3000, E=60000, seed=0, weights=False, dtype=torch.int64):
 
 
 # ------------------------------------------------------------------ extract
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3, 7])
 @pytest.mark.parametrize("dim,dtype", [(100, torch.float32), (128, torch.float32),
                                        (256, torch.bfloat16), (4, torch.float32),
-                                       (36, torch.int64)])
+                                       (36, torch.int64), (260, torch.float32)])
 def test_index_select_bit_exact(dgs, cuda, algo, dim, dtype):
     N, R = 20000, 70001
     ids = torch.arange(N)
@@ -167,7 +167,7 @@ def test_loc_table_identical_cache_lists(dgs, cuda, P):
     assert rc != 0 and b"distinct" in lib.dgs_last_error()
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 7])
 @pytest.mark.parametrize("P,rank", [(1, 0), (2, 1), (4, 2), (8, 7)])
 def test_extract_p2p_virtual_ranks_bit_exact(dgs, cuda, P, rank, algo):
     """Multi-rank cached extract emulated on one GPU: every emulated rank's shard is a tensor of this
@@ -1084,6 +1084,57 @@ def test_build_blocks_csc(dgs, cuda, idt):
         dgs.ops.coo_rows_to_indptr(torch.tensor([3, 1], dtype=idt, device=cuda), 4, check_sorted=True)
     with pytest.raises(RuntimeError, match="ascending"):
         dgs.ops.coo_rows_to_indptr(torch.tensor([1, 4], dtype=idt, device=cuda), 4, check_sorted=True)
+
+
+def test_guard_bands_stay_untouched(dgs, cuda):
+    """compute-sanitizer is closed on the GPU pool, so out-of-bounds WRITES are hunted with guard
+    bands: every output / workspace handed to the C-ABI sits inside a larger buffer filled with a
+    sentinel, and the bands on both sides must be intact afterwards (extract: every algo and odd row
+    counts; whole-batch sampling: arena, counts and workspace)."""
+    import ctypes as C
+    from dgs import _lib
+    from dgs._util import stream
+    l = _lib.lib()
+    G = 4096                                                    # guard bytes on each side
+    N, D = 5000, 100
+    feat = dgs_synth.feature_rows(torch.arange(N), D).to(cuda)
+    g = torch.Generator().manual_seed(3)
+    for algo in (1, 2, 3, 7):
+        for R in (1, 31, 33, 4097):
+            nids = torch.randint(0, N, (R,), generator=g).to(cuda)
+            buf = torch.full((2 * G + R * D * 4,), 0xA5, dtype=torch.uint8, device=cuda)
+            _lib.check(l.dgs_index_select(feat.data_ptr(), D * 4, 1, nids.data_ptr(), R,
+                                          buf.data_ptr() + G, algo, stream()))
+            assert bool((buf[:G] == 0xA5).all()) and bool((buf[G + R * D * 4:] == 0xA5).all()), (algo, R)
+            assert torch.equal(buf[G:G + R * D * 4].view(torch.float32).reshape(R, D), feat[nids])
+    indptr, indices, _ = dgs_synth.make_csr(N, 120000, seed=9)
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    pipe = smp._pipe
+    fan = [10, 5]
+    for B, S in ((1, 300), (3, 200)):
+        pl = pipe._plan_many(B, S, fan)
+        L, es = 2, 8
+        nbytes = B * pl["total"] * es + B * 2 * L * 8
+        arena = torch.full((2 * G + nbytes,), 0xA5, dtype=torch.uint8, device=cuda)
+        ws = torch.full((2 * G + pl["ws_bytes"],), 0xA5, dtype=torch.uint8, device=cuda)
+        fo = _lib.i64_array(fan)
+        _lib.check(l.dgs_sample_blocks_multi_ws_init(ws.data_ptr() + G, pl["ws_bytes"], 1, B, S, L, fo, N, stream()))
+        seeds = torch.randint(0, N, (B, S), generator=g).to(cuda)
+        base = arena.data_ptr() + G
+        for li, (of, orow, ocol) in enumerate(pl["offs"]):
+            pl["a_fr"][li], pl["a_row"][li], pl["a_col"][li] = base + of * es, base + orow * es, base + ocol * es
+        rng = (C.c_uint64 * B)(*range(1, B + 1))
+        for _ in range(3):
+            _lib.check(l.dgs_sample_blocks_multi(C.byref(pipe._graph), B, seeds.data_ptr(), S * es, S, L, fo, 0, rng,
+                                                 pl["a_fr"], pl["a_row"], pl["a_col"], pl["total"] * es,
+                                                 pl["cap_edges"], pl["cap_front"], base + B * pl["total"] * es,
+                                                 ws.data_ptr() + G, pl["ws_bytes"], pl["counts_ptr"], 1, stream()))
+        torch.cuda.synchronize()
+        for t, n in ((arena, nbytes), (ws, pl["ws_bytes"])):
+            assert bool((t[:G] == 0xA5).all()) and bool((t[G + n:] == 0xA5).all()), (B, S)
+        ref = smp._CAPI_sample_node_classifiction(seeds[B - 1], fan, False, rng_seed=B)
+        cnt = pl["counts_np"].tolist()[(B - 1) * 4:B * 4]
+        assert cnt == [ref[0][2].numel(), ref[0][1].numel(), ref[1][2].numel(), ref[1][1].numel()]
 
 
 def test_p2p_server_single_rank(dgs, cuda):

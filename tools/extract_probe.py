@@ -17,7 +17,7 @@ import dgs  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--algos", default="1,2,3,4,5,6")
+    ap.add_argument("--algos", default="1,2,3,7")
     ap.add_argument("--rows", default="192000,1000000")
     ap.add_argument("--table-rows", type=int, default=2_449_029)
     ap.add_argument("--reps", type=int, default=20)
