@@ -646,7 +646,8 @@ def run_b200(args, fan_out):
     # ---- B mini-batches per launch ("e2e_pipelined"): the loader takes B seed batches at once
     pipelined = None
     B = args.prefetch
-    if B > 1 and hasattr(loader, "load_many"):
+    many_ok = B > 1 and pipe._plan_many(B, args.batch, fan_out)["ws"] is not None
+    if many_ok:
         base = 3 * (K + W) + 2
         groups = [seeds_pin[base + j * B: base + (j + 1) * B] for j in range(K + W + 2)]
 
@@ -668,10 +669,12 @@ def run_b200(args, fan_out):
                              "single calls with the same RNG seeds"}
         # the multi-batch sampling kernel alone, back to back
         sd = [g.to(dev) for g in groups[:K + 2]]
-        keep = [loader.enqueue_many_only(sd[j], fan_out) for j in range(2)]
+        for j in range(2):
+            keep = loader.enqueue_many_only(sd[j], fan_out)
         barrier()
         x0.record()
-        keep = [loader.enqueue_many_only(sd[2 + j], fan_out) for j in range(K)]
+        for j in range(K):     # (each arena is released as the next one is allocated: stream-ordered reuse)
+            keep = loader.enqueue_many_only(sd[2 + j], fan_out)
         x1.record()
         torch.cuda.synchronize()
         pipelined["sample_kernel_ms_per_batch"] = x0.elapsed_time(x1) / (K * B)

@@ -1593,7 +1593,11 @@ static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t se
     ub += ub * k;
   }
   static const char *split_env = getenv("DGS_MB_SPLIT");   // "0" / "1": force one / many kernels
-  const bool split = split_env ? split_env[0] == '1' : B >= 2;
+  // B >= 2, or one batch that is big by itself (friendster: 4096 seeds, [20,15,10] = 14 M padded slots
+  // in the last hop): throughput work, better served by full-occupancy phase kernels than by the
+  // latency-oriented cooperative kernel
+  const bool big = (int64_t)B * a.hop[L - 1].S_ub * a.hop[L - 1].k >= (4ll << 20);
+  const bool split = split_env ? split_env[0] == '1' : (B >= 2 || big);
   if (split) {
     // one kernel per phase (see mb_pick_kernel): 3 L launches shared by the B batches
     size_t pref_max = 0;

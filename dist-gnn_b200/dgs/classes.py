@@ -11,6 +11,7 @@ from ._util import (ID_DTYPES, check_cpu, check_cuda, check_device_readable, con
 lib = _lib.lib
 check = _lib.check
 MAX_FUSED_ELEMS = 1 << 28  # ids in the worst-case arena of the fused whole-batch path (2 GiB of int64)
+MAX_MANY_ELEMS = 1 << 30   # same for one B-batch launch (8 GiB of int64: friendster, b 4096, B 8 = 2.9 GiB)
 
 
 class _NoCtx:
@@ -396,7 +397,7 @@ class _BlockPipeline:
             fo = _lib.i64_array(fan_out)
             it = ID_DTYPES[self._id_dtype]
             nbytes = -1
-            if B * total <= MAX_FUSED_ELEMS and all(k > 0 for k in fan_out):
+            if B * total <= MAX_MANY_ELEMS and all(k > 0 for k in fan_out):
                 nbytes = l.dgs_sample_blocks_multi_ws_bytes(it, B, S, L, fo, self._graph.num_nodes)
             if nbytes < 0:
                 pl = {"ws": None}
