@@ -64,11 +64,14 @@ struct __align__(16) RlSlot {
 // {first, lrank} per node, no key, no probing, and an insert is ONE fire-and-forget atomicMin
 // instead of a CAS whose result the thread has to wait for plus an atomicMin (measured on B200,
 // products shape: 93 vs 107 us per batch).  180 GB of HBM pay for 16 bytes per node.
+// direct == 2 (multi-batch kernel): 4 bytes per node, {tag:8 | first item:24} only - the rank of a
+// first occurrence lives in a per-item side array instead (HopState::lrank_at), which halves the
+// footprint the random atomics / reads of a hop cycle through L2.
 struct Tab {
   char *base;
   int direct;
   __device__ __forceinline__ unsigned int *first(uint64_t pos) const {
-    return reinterpret_cast<unsigned int *>(base + (direct ? pos * 8 : pos * 16 + 8));
+    return reinterpret_cast<unsigned int *>(base + (direct == 2 ? pos * 4 : (direct ? pos * 8 : pos * 16 + 8)));
   }
   __device__ __forceinline__ unsigned int *lrank(uint64_t pos) const { return first(pos) + 1; }
   __device__ __forceinline__ unsigned long long *key(uint64_t pos) const {
@@ -90,6 +93,11 @@ struct HopState {        // per-hop arrays that must survive until the next hop'
   unsigned int *pos_seed;  // [S_max]   table slot of seed i
   unsigned int *pos_col;   // [E_max]   table slot of padded neighbour slot e
   Tab table;
+  // compact tables (Tab::direct == 2) only: what the rank phase learns per item, so that the emit
+  // phase never goes back to the table
+  unsigned int *fslot;     // [E_max]          first-occurrence item of the id in padded slot e
+  unsigned int *fseed;     // [S_max]          same for seed i (hop 0 only: later seeds are distinct)
+  unsigned int *lrank_at;  // [S_max + E_max]  rank inside its tile of the first occurrence at item x
 };
 
 struct BlocksWs {
@@ -158,6 +166,7 @@ static int blocks_plan(int itype, int64_t num_seeds, int L, const int64_t *fan_o
   }
   p->bytes = off;
   if (ws) {
+    memset(ws, 0, sizeof(*ws));
     ws->done = (unsigned int *)done;
     ws->pending_S = (long long *)(done + 64);
     ws->prefA = (long long *)pa;
@@ -646,8 +655,15 @@ __device__ __forceinline__ void rank_one_tile(int64_t tile, int64_t S_ub, int64_
   }
   __syncthreads();
   // seeds that are a previous frontier are distinct: each is its own first occurrence
-  if (tid < ns)
-    fa = (unique_seeds || ldcg(cur.table.first(slot_a)) == ((unsigned int)(i0 + tid) | tagbits)) ? 1 : 0;
+  if (tid < ns) {
+    if (unique_seeds) {
+      fa = 1;
+    } else {
+      const unsigned int f = ldcg(cur.table.first(slot_a));
+      fa = f == ((unsigned int)(i0 + tid) | tagbits) ? 1 : 0;
+      if (kNoPos) cur.fseed[i0 + tid] = f & 0x00ffffffu;
+    }
+  }
   long long carry = 0;
   long long totA = 0, totC = 0;
   for (int base = 0; base < items || base == 0; base += kBkThreads * kRkItems) {
@@ -674,7 +690,11 @@ __device__ __forceinline__ void rank_one_tile(int64_t tile, int64_t S_ub, int64_
       const long long rac = block_exclusive_scan<long long>((fa << 32) | c, s_scan, &s_total);
       totA = s_total >> 32;
       totC = s_total & 0xffffffffll;
-      if (fa && !(kNoPos && unique_seeds)) *cur.table.lrank(slot_a) = (unsigned int)(rac >> 32);
+      if (kNoPos) {
+        if (fa && !unique_seeds) cur.lrank_at[i0 + tid] = (unsigned int)(rac >> 32);
+      } else if (fa) {
+        *cur.table.lrank(slot_a) = (unsigned int)(rac >> 32);
+      }
       if (tid < ns) ws.loff[i0 + tid] = (int)(rac & 0xffffffffll);
     }
     int mine = 0;
@@ -683,11 +703,18 @@ __device__ __forceinline__ void rank_one_tile(int64_t tile, int64_t S_ub, int64_
     for (int u = 0; u < kRkItems; ++u) {
       fb[u] = valid[u] && first[u] == ((unsigned int)(S_ub + e0 + el0 + u) | tagbits);
       mine += fb[u] ? 1 : 0;
+      if (kNoPos && valid[u]) cur.fslot[e0 + el0 + u] = first[u] & 0x00ffffffu;
     }
     long long r = carry + block_exclusive_scan<long long>((long long)mine, s_scan, &s_total);
 #pragma unroll
-    for (int u = 0; u < kRkItems; ++u)
-      if (fb[u]) *cur.table.lrank(slot[u]) = (unsigned int)(r++);
+    for (int u = 0; u < kRkItems; ++u) {
+      if (fb[u]) {
+        if (kNoPos)
+          cur.lrank_at[S_ub + e0 + el0 + u] = (unsigned int)(r++);
+        else
+          *cur.table.lrank(slot[u]) = (unsigned int)(r++);
+      }
+    }
     carry += s_total;
   }
   if (tid == 0) {
@@ -1068,7 +1095,18 @@ __device__ __forceinline__ T *off_ptr(T *p, int64_t bo) {
   return (T *)((char *)p + bo);
 }
 __device__ __forceinline__ Tab tab_of(const BlocksWs &w0, int64_t bo) {
-  return Tab{w0.hop[0].table.base + bo, 1};
+  return Tab{w0.hop[0].table.base + bo, 2};
+}
+__device__ __forceinline__ HopState hop_of_batch(const BlocksWs &w0, int64_t bo) {
+  HopState h;
+  h.cnt = off_ptr(w0.hop[0].cnt, bo);
+  h.pos_seed = nullptr;
+  h.pos_col = nullptr;
+  h.table = tab_of(w0, bo);
+  h.fslot = off_ptr(w0.hop[0].fslot, bo);
+  h.fseed = off_ptr(w0.hop[0].fseed, bo);
+  h.lrank_at = off_ptr(w0.hop[0].lrank_at, bo);
+  return h;
 }
 constexpr unsigned int kItemMask = 0x00ffffffu;   // low 24 bits of `first`: the item index
 __device__ __forceinline__ BlocksWs ws_of_batch(const BlocksWs &w0, int64_t bo) {
@@ -1080,10 +1118,7 @@ __device__ __forceinline__ BlocksWs ws_of_batch(const BlocksWs &w0, int64_t bo) 
   w.prefC = off_ptr(w0.prefC, bo);
   w.loff = off_ptr(w0.loff, bo);
   w.pad_col = off_ptr(reinterpret_cast<char *>(w0.pad_col), bo);
-  w.hop[0].cnt = w.hop[1].cnt = off_ptr(w0.hop[0].cnt, bo);
-  w.hop[0].pos_seed = w.hop[1].pos_seed = nullptr;
-  w.hop[0].pos_col = w.hop[1].pos_col = nullptr;
-  w.hop[0].table = w.hop[1].table = Tab{w0.hop[0].table.base + bo, 1};
+  w.hop[0] = w.hop[1] = hop_of_batch(w0, bo);
   w.cap = w0.cap;
   w.direct = 1;
   return w;
@@ -1129,7 +1164,15 @@ __device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, 
   const unsigned int tagbits = (a.tag0 - (unsigned int)l) << 24;
   long long S_total = 0;
   for (int b = 0; b < B; ++b) S_total += sh.S[b];
-  const int ts = pick_tile_seeds(S_total);
+  // seeds per tile: small enough that every CTA gets a tile, large enough that the tiles of all
+  // batches (each batch rounds up on its own) still fit ONE round of the grid
+  int ts;
+  {
+    const int64_t ctas = max((int64_t)1, G - B);
+    int64_t per = (S_total + ctas - 1) / ctas;
+    per = (per + 7) & ~7ll;
+    ts = (int)max((int64_t)8, min((int64_t)kPkSeeds, per));
+  }
   long long toff = 0;
   for (int b = 0; b < B; ++b) {
     const int64_t S = sh.S[b];
@@ -1138,11 +1181,7 @@ __device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, 
     toff += tiles;
     if (t0 >= tiles) continue;
     const int64_t bo = (int64_t)b * a.ws_stride;
-    HopState cur;
-    cur.cnt = off_ptr(ws0.hop[0].cnt, bo);
-    cur.pos_seed = nullptr;
-    cur.pos_col = nullptr;
-    cur.table = tab_of(ws0, bo);
+    const HopState cur = hop_of_batch(ws0, bo);
     const uint64_t key = a.rng[b] + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
     pick_tile_phase<IdT, ET, MODE, true>(
         g, off_ptr(seeds0, (int64_t)b * in_stride), S_ub, S, k, key,
@@ -1173,11 +1212,7 @@ __device__ __forceinline__ void mb_rank(const BlocksWs &ws0, const MbArgs &a, in
     if (t0 >= tiles) continue;
     const int64_t bo = (int64_t)b * a.ws_stride;
     const BlocksWs w = ws_of_batch(ws0, bo);
-    HopState cur;
-    cur.cnt = w.hop[0].cnt;
-    cur.pos_seed = nullptr;
-    cur.pos_col = nullptr;
-    cur.table = tab_of(ws0, bo);
+    const HopState cur = w.hop[0];
     const IdT *seeds_b = off_ptr(seeds0, (int64_t)b * in_stride);
     for (int64_t tile = t0; tile < tiles; tile += G) {
       rank_one_tile<IdT, true>(tile, S_ub, S, k, cur, w, unique_seeds, seeds_b, (const IdT *)w.pad_col,
@@ -1219,16 +1254,21 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
   unsigned int *sp = reinterpret_cast<unsigned int *>(dyn_smem);
   const int tiles_ub = (int)((S_ub + kBkTile - 1) / kBkTile + 1);   // entries per array
   if (smem_pref) {
-    for (int b = 0; b < B; ++b) {
-      const int64_t bo = (int64_t)b * ws_stride;
-      const long long *gA = off_ptr(ws0.prefA, bo), *gB = off_ptr(ws0.prefB, bo),
-                      *gC = off_ptr(ws0.prefC, bo);
-      const int n = (int)((sh.S[b] + kBkTile - 1) / kBkTile + 1);
-      unsigned int *pa = sp + (size_t)b * 3 * tiles_ub;
-      for (int t = tid; t < n; t += kBkThreads) {
-        pa[t] = (unsigned int)ldcg(gA + t);
-        pa[tiles_ub + t] = (unsigned int)ldcg(gB + t);
-        pa[2 * tiles_ub + t] = (unsigned int)ldcg(gC + t);
+    // one flat loop over (batch, tile): a loop over the batches would be B dependent round trips
+    // (measured: the emit phase of a tiny hop took 19 us at B = 16 instead of 4)
+    const int total = B * tiles_ub;
+#pragma unroll 4
+    for (int i = tid; i < total; i += kBkThreads) {
+      const int b = i / tiles_ub, t = i - b * tiles_ub;
+      if (t < (int)((sh.S[b] + kBkTile - 1) / kBkTile + 1)) {
+        const int64_t bo = (int64_t)b * ws_stride;
+        unsigned int *pa = sp + (size_t)b * 3 * tiles_ub;
+        const unsigned int va = (unsigned int)ldcg(off_ptr(ws0.prefA, bo) + t);
+        const unsigned int vb = (unsigned int)ldcg(off_ptr(ws0.prefB, bo) + t);
+        const unsigned int vc = (unsigned int)ldcg(off_ptr(ws0.prefC, bo) + t);
+        pa[t] = va;
+        pa[tiles_ub + t] = vb;
+        pa[2 * tiles_ub + t] = vc;
       }
     }
   }
@@ -1273,11 +1313,10 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
     const IdT sid = ldcg(off_ptr(seeds0, (int64_t)b * in_stride) + i);
     IdT *frontier = off_ptr(frontier0, (int64_t)b * out_stride);
     const int64_t bo = (int64_t)b * ws_stride;
-    const int2 fl = tab_of(ws0, bo).first_lrank((uint64_t)sid);
-    if (((unsigned int)fl.x & kItemMask) == i) {
+    if (ldcg(off_ptr(ws0.hop[0].fseed, bo) + i) == i) {       // first occurrence of this seed id
       const unsigned int pa = smem_pref ? sp[(size_t)b * 3 * tiles_ub + i / kBkTile]
                                         : (unsigned int)ldcg(off_ptr(ws0.prefA, bo) + i / kBkTile);
-      frontier[pa + (unsigned int)fl.y] = sid;
+      frontier[pa + ldcg(off_ptr(ws0.hop[0].lrank_at, bo) + i)] = sid;
     }
   }
   // padded slots -> compacted, relabelled COO (+ frontier entries of first occurrences)
@@ -1288,7 +1327,7 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
     int bb[EB];
     unsigned int ee[EB], si[EB];
     bool ok[EB];
-    IdT cidv[EB], sidv[EB];
+    unsigned int cf[EB], cr[EB], sf[EB], sr[EB];
 #pragma unroll
     for (int u = 0; u < EB; ++u) {
       const int64_t v = base + u * stride;
@@ -1301,21 +1340,18 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
         ee[u] = e;
         si[u] = e / uk;
         ok[u] = (e - si[u] * uk) < (unsigned int)ldcg(off_ptr(ws0.hop[0].cnt, bo) + si[u]);
-        cidv[u] = ldcg(reinterpret_cast<const IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)) + e);
-        if (!unique_seeds) sidv[u] = ldcg(off_ptr(seeds0, (int64_t)b * in_stride) + si[u]);
+        // what the rank phase recorded: first-occurrence item of this slot's id (and of its seed)
+        cf[u] = ldcg(off_ptr(ws0.hop[0].fslot, bo) + e);
+        if (!unique_seeds) sf[u] = ldcg(off_ptr(ws0.hop[0].fseed, bo) + si[u]);
       }
     }
-    unsigned int cf[EB], cr[EB], sf[EB], sr[EB];
 #pragma unroll
     for (int u = 0; u < EB; ++u) {
       if (ok[u]) {
-        const Tab tb = tab_of(ws0, (int64_t)bb[u] * ws_stride);
-        const int2 c2 = tb.first_lrank((uint64_t)cidv[u]);
-        cf[u] = (unsigned int)c2.x & kItemMask; cr[u] = (unsigned int)c2.y;
-        if (!unique_seeds) {
-          const int2 s2 = tb.first_lrank((uint64_t)sidv[u]);
-          sf[u] = (unsigned int)s2.x & kItemMask; sr[u] = (unsigned int)s2.y;
-        }
+        const int64_t bo = (int64_t)bb[u] * ws_stride;
+        // rank of that first occurrence inside its tile (not needed for a distinct seed: id = index)
+        cr[u] = (unique_seeds && (int64_t)cf[u] < S_ub) ? 0u : ldcg(off_ptr(ws0.hop[0].lrank_at, bo) + cf[u]);
+        if (!unique_seeds) sr[u] = ldcg(off_ptr(ws0.hop[0].lrank_at, bo) + sf[u]);
       }
     }
 #pragma unroll
@@ -1340,7 +1376,9 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
           cid = unique_seeds ? f : PA(f / kBkTile) + cr[u];
         else
           cid = PA(tiles) + PB((unsigned int)((f - (unsigned int)S_ub) / uk) / kBkTile) + cr[u];
-        if ((int64_t)f == S_ub + (int64_t)e) off_ptr(frontier0, (int64_t)b * out_stride)[cid] = cidv[u];
+        if ((int64_t)f == S_ub + (int64_t)e)      // this slot IS the first occurrence: it names the id
+          off_ptr(frontier0, (int64_t)b * out_stride)[cid] =
+              ldcg(reinterpret_cast<const IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)) + e);
         const unsigned int rid = unique_seeds ? s_i : PA(sf[u] / kBkTile) + sr[u];
         const unsigned int o = PC(s_i / kBkTile) + (unsigned int)ldcg(off_ptr(ws0.loff, bo) + s_i) + j;
         off_ptr(row0, (int64_t)b * out_stride)[o] = (IdT)rid;
@@ -1510,8 +1548,8 @@ static int multi_plan(int itype, int B, int64_t num_seeds, int L, const int64_t 
   p->S_max = S_max;
   p->E_max = E_max;
   p->tiles_max = (S_max + kBkTile - 1) / kBkTile;
-  p->cap = (num_nodes + 1) & ~1ll;
-  p->table_bytes = p->cap * 8;
+  p->cap = (num_nodes + 3) & ~3ll;
+  p->table_bytes = p->cap * 4;          // {tag:8 | first item:24} per node
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
     char *q = base ? base + off : nullptr;
@@ -1524,6 +1562,7 @@ static int multi_plan(int itype, int B, int64_t num_seeds, int L, const int64_t 
   char *cnt = take(S_max * 4);
   char *loff = take(S_max * 4);
   char *pad = take(E_max * idb);
+  char *fslot = take(E_max * 4), *fseed = take(S_max * 4), *lrank_at = take((S_max + E_max) * 4);
   char *t0 = take(p->table_bytes);
   p->stride = off;
   p->bytes = off * B;
@@ -1541,7 +1580,10 @@ static int multi_plan(int itype, int B, int64_t num_seeds, int L, const int64_t 
       ws->hop[b].pos_seed = nullptr;
       ws->hop[b].pos_col = nullptr;
       ws->hop[b].table.base = t0;
-      ws->hop[b].table.direct = 1;
+      ws->hop[b].table.direct = 2;
+      ws->hop[b].fslot = (unsigned int *)fslot;
+      ws->hop[b].fseed = (unsigned int *)fseed;
+      ws->hop[b].lrank_at = (unsigned int *)lrank_at;
     }
     ws->cap = p->cap;
     ws->direct = 1;

@@ -13,9 +13,37 @@
 // Why not a CUDA graph: the outputs of a batch are fresh caller-owned buffers and the RNG key
 // changes, so every node's parameters differ from step to step - an exec-update per launch costs
 // the CPU about what the five plain launches cost.
+#include <chrono>
+
 #include "dgs_common.cuh"
 
 using namespace dgsb;
+
+// DGS_LOADER_TRACE=1: host-clock breakdown of the call (us, averaged over 100 calls) on stderr
+namespace {
+struct LoaderTrace {
+  bool on = getenv("DGS_LOADER_TRACE") != nullptr;
+  double acc[8] = {0};
+  int n = 0;
+  std::chrono::steady_clock::time_point t;
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void lap(int i) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  void done() {
+    if (!on || ++n < 100) return;
+    fprintf(stderr, "[dgs loader trace us] h2d %.1f sample-enqueue %.1f extract-enqueue %.1f labels %.1f "
+            "wait-counts %.1f stream-sync %.1f\n", acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n,
+            acc[5] / n);
+    for (double &a : acc) a = 0;
+    n = 0;
+  }
+};
+LoaderTrace g_trace;
+}  // namespace
 
 extern "C" int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, const void *seeds,
                               int seeds_on_host, void *seeds_dev, int64_t num_seeds, int num_layers,
@@ -33,6 +61,7 @@ extern "C" int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, con
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t es = g->itype == DGS_I64 ? 8 : 4;
   const void *sd = seeds;
+  g_trace.start();
   if (seeds_on_host) {
     DGS_CUDA_OK(cudaMemcpyAsync(seeds_dev, seeds, (size_t)(num_seeds * es), cudaMemcpyHostToDevice, st));
     sd = seeds_dev;
@@ -45,15 +74,18 @@ extern "C" int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, con
     col[l] = base + hop_offsets[3 * l + 2] * es;
   }
   int64_t *counts_dev = (int64_t *)(base + counts_offset * es);
+  g_trace.lap(0);
   int rc = dgs_sample_blocks_enqueue(g, sd, num_seeds, num_layers, fan_out, replace, rng_seed, fr, row, col,
                                      cap_edges, cap_frontier, counts_dev, ws, ws_bytes, epoch, counts_host,
                                      stream);
   if (rc) return rc;
+  g_trace.lap(1);
   // extract of the last hop's frontier: its live size is counts_dev[2 L - 1]
   rc = dgs_extract_dyn(f->table, f->feat, f->loc_table, f->loc_capacity, f->mod_world, f->row_bytes,
                        g->itype, fr[num_layers - 1], x_rows_ub, counts_dev + 2 * num_layers - 1, x_out, algo,
                        stream);
   if (rc) return rc;
+  g_trace.lap(2);
   if (f->labels != nullptr && labels_out_dev != nullptr) {
     rc = dgs_index_select(f->labels, f->label_bytes, g->itype, sd, num_seeds, labels_out_dev, 1, stream);
     if (rc) return rc;
@@ -61,9 +93,13 @@ extern "C" int dgs_load_batch(const dgs_graph_t *g, const dgs_features_t *f, con
       DGS_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels_out_dev, (size_t)(num_seeds * f->label_bytes),
                                   cudaMemcpyDeviceToHost, st));
   }
+  g_trace.lap(3);
   // the one host round trip: hop sizes (the extract / label work enqueued above may still run)
   rc = dgs_sample_blocks_wait(counts_host, counts_dev, num_layers, stream);
   if (rc) return rc;
+  g_trace.lap(4);
   if (f->labels != nullptr && labels_out_host != nullptr) DGS_CUDA_OK(cudaStreamSynchronize(st));
+  g_trace.lap(5);
+  g_trace.done();
   return 0;
 }
