@@ -680,6 +680,8 @@ def run_b200(args, fan_out):
         pipelined["sample_kernel_ms_per_batch"] = x0.elapsed_time(x1) / (K * B)
         pipelined["sample_kernel_frac_of_hbm"] = (sm_bytes / K) / (pipelined["sample_kernel_ms_per_batch"]
                                                                   * 1e-3) / 1e9 / peaks()[0]
+        pipelined["sample_kernels"] = ("mb_pick_kernel / mb_rank_kernel / mb_emit_kernel: one launch per "
+                                       "phase and hop, shared by the B batches (3 L launches)")
         del keep, sd
     clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through the timed regions
 
@@ -759,7 +761,7 @@ def run_b200(args, fan_out):
                              "nvlink_frac": peer / 900.0,
                              "note": "remote fraction (P-1)/P of the gathered row bytes / slowest "
                                      "rank's kernel time, against 900 GB/s NVLink ingress per GPU"})
-    roof_sample = {"bound": "hbm", "kernel": "fused_batch_kernel (all hops: sample + relabel, one "
+    roof_sample = {"bound": "hbm", "kernel": "multi_batch_kernel (all hops: sample + relabel, one "
                                              "cooperative launch per batch)",
                    "achieved": sm_gbs, "peak": peak, "unit": "GB/s", "frac": sm_gbs / peak,
                    "peak_source": peak_src, "traffic": traffic.get("sample"),
