@@ -372,7 +372,6 @@ constexpr int kPkSeeds = 128;  // seeds per pick tile (256 was slower on B200: 4
 constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase (8: no gain)
 constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
-constexpr int kFloydRegs = 16; // fan-outs up to this run Floyd's sampling in registers
 constexpr int kHubDeg = 512;   // biased sampling: rows longer than this are scanned by the whole CTA (measured: 2048 slower)
 
 // Seeds per pick tile: up to 128, fewer when the hop is small so that every CTA of the grid gets
@@ -401,11 +400,43 @@ struct PosEmit {
 //   B2 thread per slot : neighbour load, padded store, table insert - 8 independent
 //      load -> CAS chains in flight per thread
 // Same RNG counters as the warp-per-seed kernel => identical samples.
+// Floyd's subset sampling entirely in registers (fully unrolled, no shared-memory round trips):
+// draw t picks r in [0, deg-k+t], or deg-k+t itself when r was already picked.  R = register slots
+// (k <= R); the positions go to dst[0..k).
+template <int R>
+__device__ __forceinline__ void floyd_in_registers(uint64_t rng_key, uint64_t item, int deg, int k,
+                                                   unsigned int *__restrict__ dst) {
+  unsigned int P[R];
+#pragma unroll
+  for (int q = 0; q < R / 4; ++q) {
+    if (4 * q < k) {
+      const uint4 r4 = Philox::gen(rng_key, item, (uint64_t)q);
+      P[4 * q] = r4.x; P[4 * q + 1] = r4.y; P[4 * q + 2] = r4.z; P[4 * q + 3] = r4.w;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < R; ++t) {
+    if (t < k) {
+      const unsigned int J = (unsigned int)(deg - k + t);
+      const unsigned int r = rand_below(P[t], J + 1);
+      bool dup = false;
+#pragma unroll
+      for (int q = 0; q < t; ++q) dup |= (P[q] == r);
+      P[t] = dup ? J : r;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < R; ++t)
+    if (t < k) dst[t] = P[t];
+}
+
 // kNoPos (direct tables only): the table slot of an id IS the id, so the slot arrays pos_seed /
 // pos_col are neither written here nor read by the later phases.  ts = seeds per tile; the CTA owns
 // tiles tile0, tile0 + tstride, ...  tagbits: OR-ed into every item index stored in the table
-// (epoch tag of the multi-batch kernel's never-wiped tables; 0 elsewhere).
-template <typename IdT, typename ET, int MODE, bool kNoPos = false>
+// (epoch tag of the multi-batch kernel's never-wiped tables; 0 elsewhere).  FR: fan-outs up to FR
+// run Floyd's sampling in registers (32 costs the 128-register cooperative kernel spills, measured
+// +5 us per batch at k <= 16, so only the stand-alone pick kernel of large fan-outs uses it).
+template <typename IdT, typename ET, int MODE, bool kNoPos = false, int FR = 16>
 __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__restrict__ seeds,
                                                 int64_t S_ub, int64_t S, int k, uint64_t rng_key,
                                                 IdT *__restrict__ pad_col, const HopState &cur,
@@ -464,36 +495,16 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
       s_deg[tid] = deg;
       s_cnt[tid] = cnt;
       cur.cnt[i] = cnt;
-      if (MODE == kUniform && k <= kFloydRegs && deg > k) {
-        // Floyd's subset sampling entirely in registers (fully unrolled, no shared-memory round
-        // trips): draw t picks r in [0, deg-k+t], or deg-k+t itself when r was already picked
-        unsigned int P[kFloydRegs];
-#pragma unroll
-        for (int q = 0; q < kFloydRegs / 4; ++q) {
-          if (4 * q < k) {
-            const uint4 r4 = Philox::gen(rng_key, (uint64_t)i, (uint64_t)q);
-            P[4 * q] = r4.x; P[4 * q + 1] = r4.y; P[4 * q + 2] = r4.z; P[4 * q + 3] = r4.w;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < kFloydRegs; ++t) {
-          if (t < k) {
-            const unsigned int J = (unsigned int)(deg - k + t);
-            const unsigned int r = rand_below(P[t], J + 1);
-            bool dup = false;
-#pragma unroll
-            for (int q = 0; q < t; ++q) dup |= (P[q] == r);
-            P[t] = dup ? J : r;
-          }
-        }
+      if (MODE == kUniform && k <= FR && deg > k) {
         unsigned int *dst = s_pick + (size_t)tid * k;
-#pragma unroll
-        for (int t = 0; t < kFloydRegs; ++t)
-          if (t < k) dst[t] = P[t];
+        if (FR <= 16 || k <= 16)
+          floyd_in_registers<16>(rng_key, (uint64_t)i, deg, k, dst);
+        else
+          floyd_in_registers<32>(rng_key, (uint64_t)i, deg, k, dst);   // friendster's k = 20
       }
     }
     if (tile == tile0) fstamp(1);
-    if (MODE == kUniform && k > kFloydRegs) {
+    if (MODE == kUniform && k > FR) {
       // random words of Floyd's draws, computed by all threads (one Philox block = 4 draws)
       const int blocks_per_seed = (k + 3) >> 2;
       for (int b = tid; b < ns * blocks_per_seed; b += kBkThreads) {
@@ -507,8 +518,8 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         if (left > 3) P[3] = r4.w;
       }
     }
-    if (MODE != kUniform || k > kFloydRegs) __syncthreads();
-    if (MODE == kUniform && k > kFloydRegs) {
+    if (MODE != kUniform || k > FR) __syncthreads();
+    if (MODE == kUniform && k > FR) {
       // Floyd's subset sampling, one THREAD per seed (O(k^2) compares against shared memory)
       if (tid < ns) {
         const int deg = s_deg[tid];
@@ -1152,7 +1163,7 @@ __device__ __forceinline__ void mb_load_S(const MbArgs &a, int l, MbShared &sh) 
 }
 
 // ---------------- pick: virtual tiles of all batches, dealt round-robin to the CTAs
-template <typename IdT, typename ET, int MODE>
+template <typename IdT, typename ET, int MODE, int FR = 16>
 __device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, const MbArgs &a, int l,
                                         MbShared &sh) {
   const int B = a.B;
@@ -1183,7 +1194,7 @@ __device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, 
     const int64_t bo = (int64_t)b * a.ws_stride;
     const HopState cur = hop_of_batch(ws0, bo);
     const uint64_t key = a.rng[b] + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
-    pick_tile_phase<IdT, ET, MODE, true>(
+    pick_tile_phase<IdT, ET, MODE, true, FR>(
         g, off_ptr(seeds0, (int64_t)b * in_stride), S_ub, S, k, key,
         reinterpret_cast<IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)), cur, 0, ts, t0, G,
         tagbits);
@@ -1441,12 +1452,12 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
 #ifndef DGS_MB_PICK_CTAS
 #define DGS_MB_PICK_CTAS 3  // measured at B = 8: 37.4 (2) / 36.3 (3) / 37.0 (4) us per batch
 #endif
-template <typename IdT, typename ET, int MODE>
-__global__ void __launch_bounds__(kBkThreads, DGS_MB_PICK_CTAS)
+template <typename IdT, typename ET, int MODE, int FR>
+__global__ void __launch_bounds__(kBkThreads, FR > 16 ? 2 : DGS_MB_PICK_CTAS)
 mb_pick_kernel(GraphSrc g, BlocksWs ws0, MbArgs a, int l) {
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
-  mb_pick<IdT, ET, MODE>(g, ws0, a, l, sh);
+  mb_pick<IdT, ET, MODE, FR>(g, ws0, a, l, sh);
 }
 template <typename IdT>
 __global__ void __launch_bounds__(kBkThreads, 4) mb_rank_kernel(BlocksWs ws0, MbArgs a, int l) {
@@ -1658,20 +1669,24 @@ static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t se
     for (int l = 0; l < L; ++l) {
       const int64_t k = a.hop[l].k, S_ub = a.hop[l].S_ub;
       const size_t sm_pick = (size_t)kPkSeeds * k * sizeof(int) + (mode == kBias ? (size_t)kBkWarps * k * sizeof(float) : 0);
-#define DGS_MBP(M)                                                                                   \
+#define DGS_MBP_(M, FRV, CTAS)                                                                       \
   do {                                                                                               \
-    auto kp = mb_pick_kernel<IdT, ET, M>;                                                            \
+    auto kp = mb_pick_kernel<IdT, ET, M, FRV>;                                                       \
     if (sm_pick > 32 * 1024)                                                                         \
       DGS_CUDA_OK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pick)); \
-    kp<<<sms * DGS_MB_PICK_CTAS, kBkThreads, sm_pick, st>>>(src, ws, a, l);                                         \
+    kp<<<sms * (CTAS), kBkThreads, sm_pick, st>>>(src, ws, a, l);                                    \
   } while (0)
+#define DGS_MBP(M) DGS_MBP_(M, 16, DGS_MB_PICK_CTAS)
       switch (mode) {
-        case kUniform: DGS_MBP(kUniform); break;
+        case kUniform:   // fan-outs 17..32: Floyd in 32 registers (2 CTAs per SM)
+          if (k > 16 && k <= 32) DGS_MBP_(kUniform, 32, 2); else DGS_MBP(kUniform);
+          break;
         case kUniformReplace: DGS_MBP(kUniformReplace); break;
         case kBias: DGS_MBP(kBias); break;
         default: DGS_MBP(kBiasReplace); break;
       }
 #undef DGS_MBP
+#undef DGS_MBP_
       DGS_LAUNCH_CHECK();
       const int64_t tiles = (int64_t)B * ((S_ub + kBkTile - 1) / kBkTile);
       mb_rank_kernel<IdT><<<(int)std::min<int64_t>(tiles, (int64_t)sms * 4), kBkThreads, 0, st>>>(ws, a, l);
