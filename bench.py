@@ -76,6 +76,9 @@ def parse_args():
                          "degree on every GPU (local hits replace NVLink reads; location table)")
     ap.add_argument("--prefetch", type=int, default=8,
                     help="mini-batches per launch of the pipelined leg (e2e_pipelined)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="also time BatchLoader.iter_many (sampling of group g + 1 on the main stream "
+                         "overlapped with the extracts of group g on a side stream): e2e_overlapped")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
@@ -667,6 +670,28 @@ def run_b200(args, fan_out):
                              "sampled by ONE cooperative launch (the hops of all B batches share every "
                              "phase and grid barrier), then B extracts; results bit-identical to B "
                              "single calls with the same RNG seeds"}
+        if args.overlap:
+            # N > 1: the NVLink-bound gathers keep the link busy with 2 CTAs per SM, which leaves the
+            # rest of every SM to the next group's sampling kernels (measured at 2 GPUs: 0.114 -> 0.095
+            # ms per batch; without the cap 0.108; on one GPU the HBM-bound gather and the
+            # latency-bound sampling only slow each other down, so no cap and no gain there)
+            gc = int(os.environ.get("DGS_BENCH_GATHER_CTAS", "0")) or (2 if world > 1 else None)
+            for _ in loader.iter_many(groups[:W + 2], fan_out, False, None, args.extract_algo, gc):
+                pass
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            o_edges = 0
+            e0.record()
+            for res in loader.iter_many(groups[W + 2:W + 2 + K], fan_out, False, None, args.extract_algo, gc):
+                o_edges += sum(b[2].numel() for r in res for b in r[0])
+            e1.record()
+            barrier()
+            o_ms = reduce(e0.elapsed_time(e1), "max")
+            pipelined["overlapped"] = {"ms_per_batch": o_ms / (K * B),
+                                       "value": reduce(o_edges, "sum") / (o_ms * 1e-3), "unit": UNIT,
+                                       "note": "BatchLoader.iter_many: two streams, the next group's "
+                                               "sampling overlaps this group's extracts"}
         # the multi-batch sampling kernel alone, back to back
         sd = [g.to(dev) for g in groups[:K + 2]]
         for j in range(2):
@@ -683,6 +708,25 @@ def run_b200(args, fan_out):
         pipelined["sample_kernels"] = ("mb_pick_kernel / mb_rank_kernel / mb_emit_kernel: one launch per "
                                        "phase and hop, shared by the B batches (3 L launches)")
         del keep, sd
+    # ---- N > 1: extract-only leg, 1 M random rows per GPU on all GPUs at once (the NVLink roofline
+    # at a launch size that is not dominated by the fixed cost of a mini-batch-sized launch)
+    extract_only = None
+    if world > 1 and getattr(feature_source, "_mod_world", -1) >= 0:
+        R = 1_000_000
+        g = torch.Generator().manual_seed(777 + rank)
+        qs = [torch.randint(0, N, (R,), generator=g).to(dev) for _ in range(2)]
+        outs = [extract(qs[i % 2]) for i in range(4)]
+        del outs
+        barrier()
+        x0.record()
+        outs = [extract(qs[i % 2]) for i in range(6)]
+        x1.record()
+        barrier()
+        xo_ms = reduce(x0.elapsed_time(x1), "max") / 6
+        del outs, qs
+        payload = R * row_bytes * (world - 1) / world / (xo_ms * 1e-3) / 1e9
+        extract_only = {"rows_per_gpu": R, "ms": xo_ms, "peer_payload_gbps_per_gpu": payload,
+                        "algorithmic_gbps_per_gpu": R * (2 * row_bytes + 8) / (xo_ms * 1e-3) / 1e9}
     clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through the timed regions
 
     # ---- N > 1, sharded headline: the full-replica layout (what the cache policy picks when
@@ -755,12 +799,25 @@ def run_b200(args, fan_out):
                     "traffic_source": traffic_src if traffic.get("extract") else None,
                     "algorithmic_bytes": "rows * (2 * row_bytes + 8)", "avg_launch_ms": ex_ms / K,
                     "rows_per_launch": ex_rows / K}
+    # bytes on the wire per payload byte of a peer row read, from ncu nvlrx__bytes.sum /
+    # (rows * row_bytes) (profiles/r02_nvlink_ncu.csv): whole 32-byte sectors + ~16 B of protocol per
+    # 128-byte line
+    wire = {400: 1.2562, 512: 1.125}.get(row_bytes)
     if remote_frac > 0:
         peer = ex_rows * row_bytes * remote_frac / (ex_ms_max * 1e-3) / 1e9
         roof_extract.update({"bound": "nvlink", "peer_load_gbps_per_gpu": peer, "nvlink_peak_gbps": 900,
                              "nvlink_frac": peer / 900.0,
+                             "nvlink_wire_gbps_per_gpu": peer * wire if wire else None,
+                             "nvlink_wire_frac": peer * wire / 900.0 if wire else None,
                              "note": "remote fraction (P-1)/P of the gathered row bytes / slowest "
-                                     "rank's kernel time, against 900 GB/s NVLink ingress per GPU"})
+                                     "rank's kernel time, against 900 GB/s NVLink ingress per GPU; "
+                                     "wire = payload x the ncu-measured nvlrx__bytes ratio for this "
+                                     "row size (profiles/r02_nvlink_ncu.csv)"})
+    if extract_only is not None:
+        extract_only["nvlink_frac"] = extract_only["peer_payload_gbps_per_gpu"] / 900.0
+        if wire:
+            extract_only["nvlink_wire_gbps_per_gpu"] = extract_only["peer_payload_gbps_per_gpu"] * wire
+            extract_only["nvlink_wire_frac"] = extract_only["peer_payload_gbps_per_gpu"] * wire / 900.0
     roof_sample = {"bound": "hbm", "kernel": "multi_batch_kernel (all hops: sample + relabel, one "
                                              "cooperative launch per batch)",
                    "achieved": sm_gbs, "peak": peak, "unit": "GB/s", "frac": sm_gbs / peak,
@@ -801,6 +858,7 @@ def run_b200(args, fan_out):
         "gpu_launches": launches,
         "roofline": dominant,
         "roofline_other": other,
+        "extract_only": extract_only,
         "reference_gpu": ref_gpu,
     }
     if host_graph is not None:

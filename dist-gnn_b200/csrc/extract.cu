@@ -370,6 +370,11 @@ gather_rows_tma_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Resident CTAs per SM the gather kernels ask for (default 8 = the whole SM).  A caller that runs a
+// gather next to another kernel on a second stream (BatchLoader.iter_many) lowers it so that the
+// other kernel finds room: an NVLink-bound gather needs ~2 CTAs per SM to keep the link busy.
+static int g_gather_ctas_per_sm = 8;
+
 static inline uint32_t div_magic(uint32_t d) { return (uint32_t)(((1ull << 32) + d - 1) / d); }
 
 template <typename IdT>
@@ -412,7 +417,7 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
     const uint32_t vpr = (uint32_t)(row_bytes / 16);
     int gshift = 0;
     while ((1u << gshift) < vpr && gshift < 5) ++gshift;
-    const int grid = grid_for(n, 32 * kWarpGatherWarps, 8);
+    const int grid = grid_for(n, 32 * kWarpGatherWarps, g_gather_ctas_per_sm);
     gather_rows_aligned_kernel<IdT, 8><<<grid, kWarpGatherWarps * 32, 0, st>>>(src, nids, n, row_bytes, vpr,
                                                                             gshift, out);
     DGS_LAUNCH_CHECK();
@@ -424,7 +429,7 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
     const uint32_t vpr = (uint32_t)(row_bytes / 16);
     DGS_REQUIRE((uint64_t)vpr * 32 < 65536, "extract: row_bytes %lld too large for algo %d",
                 (long long)row_bytes, algo);
-    const int grid = grid_for(n, 32 * kWarpGatherWarps, 8);
+    const int grid = grid_for(n, 32 * kWarpGatherWarps, g_gather_ctas_per_sm);
     const uint32_t magic = div_magic(vpr);
     // vectors in flight per lane (U): 13 = half of a 400-byte-row group's share per lane
 #define DGS_WG(UU, HH)                                                                          \
@@ -438,7 +443,7 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
     DGS_LAUNCH_CHECK();
     return 0;
   }
-  int grid = grid_for(n, kGatherRows, 8);
+  int grid = grid_for(n, kGatherRows, g_gather_ctas_per_sm);
   if (all_aligned16 && row_bytes % 16 == 0) {
     uint32_t vpr = (uint32_t)(row_bytes / 16);
     DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large for the "
@@ -473,6 +478,12 @@ static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; 
 }  // namespace dgsb
 
 using namespace dgsb;
+
+extern "C" int dgs_set_gather_ctas_per_sm(int ctas) {
+  DGS_REQUIRE(ctas >= 1 && ctas <= 8, "dgs_set_gather_ctas_per_sm: 1..8");
+  g_gather_ctas_per_sm = ctas;
+  return 0;
+}
 
 extern "C" int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids,
                                 int64_t n, void *out, int algo, void *stream) {

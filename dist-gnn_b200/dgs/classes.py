@@ -412,7 +412,8 @@ class _BlockPipeline:
                     offs.append((off, off + u + n, off + u + 2 * n))
                     off += u + 3 * n
                 counts_host = torch.empty(B * 2 * L, dtype=torch.int64).pin_memory()
-                pl = {"L": L, "B": B, "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "pad": total - used,
+                counts_host2 = torch.empty(B * 2 * L, dtype=torch.int64).pin_memory()   # iter_many: 2 in flight
+                pl = {"L": L, "B": B, "counts2": (counts_host2, counts_host2.numpy(), counts_host2.data_ptr()), "ubs": ubs, "nnz_ubs": nnz_ubs, "total": total, "pad": total - used,
                       "ws": ws, "ws_bytes": int(nbytes), "fo": fo, "es": es, "offs": offs,
                       "cap_edges": _lib.i64_array(nnz_ubs),
                       "cap_front": _lib.i64_array([u + n for u, n in zip(ubs, nnz_ubs)]),
@@ -426,9 +427,11 @@ class _BlockPipeline:
             self._plans[key] = pl
         return pl
 
-    def enqueue_many(self, seeds, fan_out, replace=False, rng_seeds=None, deliver_counts=True):
+    def enqueue_many(self, seeds, fan_out, replace=False, rng_seeds=None, deliver_counts=True, slot=0):
         """Enqueue B = seeds.shape[0] mini-batches (seeds: [B, S] CUDA tensor) as ONE launch.
-        Returns (plan, arena); arena = B regions of plan["total"] ids, then [B][2 L] int64 counts."""
+        Returns (plan, arena); arena = B regions of plan["total"] ids, then [B][2 L] int64 counts.
+        slot: which of the plan's two pinned count buffers the kernel reports to (two launches can
+        be in flight when the caller pipelines, BatchLoader.iter_many)."""
         l = lib()
         fan_out = [int(k) for k in fan_out]
         B, S = int(seeds.shape[0]), int(seeds.shape[1])
@@ -450,21 +453,21 @@ class _BlockPipeline:
                 C.byref(self._graph), B, seeds.data_ptr(), S * es, S, pl["L"], pl["fo"],
                 int(bool(replace)), pl["rng"], pl["a_fr"], pl["a_row"], pl["a_col"], pl["total"] * es,
                 pl["cap_edges"], pl["cap_front"], base + B * pl["total"] * es, pl["ws"].data_ptr(),
-                pl["ws_bytes"], pl["counts_ptr"] if deliver_counts else None, 0, stream()),
-                "sample_blocks_multi")
+                pl["ws_bytes"], (pl["counts2"][2] if slot else pl["counts_ptr"]) if deliver_counts else None,
+                0, stream()), "sample_blocks_multi")
         return pl, arena
 
-    def wait_many(self, pl, arena):
+    def wait_many(self, pl, arena, slot=0):
         B = pl["B"]
         with _on_device(self._device):
-            check(lib().dgs_sample_blocks_wait(pl["counts_ptr"],
+            check(lib().dgs_sample_blocks_wait(pl["counts2"][2] if slot else pl["counts_ptr"],
                                                arena.data_ptr() + B * pl["total"] * pl["es"],
                                                pl["L"] * B, stream()), "sample_blocks_wait")
 
-    def _views_many(self, pl, arena, seeds):
-        """Exact-size views of every batch's blocks from the hop sizes in pl["counts_np"]."""
+    def _views_many(self, pl, arena, seeds, slot=0):
+        """Exact-size views of every batch's blocks from the hop sizes in the pinned count buffer."""
         B, L = pl["B"], pl["L"]
-        counts = pl["counts_np"].tolist()
+        counts = (pl["counts2"][1] if slot else pl["counts_np"]).tolist()
         sizes = []
         for b in range(B):
             for li, (u, n) in enumerate(zip(pl["ubs"], pl["nnz_ubs"])):
@@ -889,6 +892,104 @@ class BatchLoader:
         B = seeds.shape[0]
         return self._pipe.enqueue_many(seeds, fan_out, replace, rng_seeds or list(range(1, B + 1)),
                                        deliver_counts=False)[1]
+
+    def iter_many(self, groups, fan_out, replace=False, rng_seeds=None, algo=0, gather_ctas_per_sm=None):
+        """Software-pipelined load_many over an iterable of seed groups ([B, S] each, pinned host or
+        CUDA): yields, per group, the list of B (blocks, features, labels) that load_many returns.
+        The sampling launch of group g + 1 is enqueued (current stream) BEFORE the host waits for
+        group g, and the extracts + label gather of a group run on a side stream behind an event -
+        so the latency-bound sampling kernels of one group overlap the bandwidth-bound (HBM or
+        NVLink) gathers of the previous one, and the host's view building overlaps both.  The
+        tensors of a yielded group are safe to use on the current stream (it waits for the group's
+        extract event).  rng_seeds: optional callable g -> list of B seeds."""
+        if getattr(self, "_xstream", None) is None:
+            self._xstream = torch.cuda.Stream(device=self._device)
+        if gather_ctas_per_sm:    # leave room on every SM for the sampling kernels of the next group
+            check(lib().dgs_set_gather_ctas_per_sm(int(gather_ctas_per_sm)), "gather_ctas_per_sm")
+        try:
+            prev = None
+            for gi, seeds in enumerate(groups):
+                cur = self._enqueue_group(seeds, fan_out, replace, rng_seeds(gi) if rng_seeds else None,
+                                          algo, slot=gi & 1)
+                if prev is not None:
+                    yield self._finish_group(prev, algo)
+                prev = cur
+            if prev is not None:
+                yield self._finish_group(prev, algo)
+        finally:
+            if gather_ctas_per_sm:
+                lib().dgs_set_gather_ctas_per_sm(8)
+
+    def _enqueue_group(self, seeds, fan_out, replace, rng_seeds, algo, slot):
+        l = lib()
+        fan_out = [int(k) for k in fan_out]
+        L = len(fan_out)
+        B, S = int(seeds.shape[0]), int(seeds.shape[1])
+        if rng_seeds is None:
+            rng_seeds = [l.dgs_randn_uint64() for _ in range(B)]
+        with _on_device(self._device):
+            if not seeds.is_cuda:
+                seeds = seeds.to(self._device, non_blocking=True)
+            seeds = seeds.contiguous()
+            pl = self._pipe._plan_many(B, S, fan_out) if (L > 0 and S > 0 and all(k > 0 for k in fan_out)) \
+                else {"ws": None}
+            if pl["ws"] is None:
+                return {"fallback": [self.load(seeds[b], fan_out, replace, rng_seeds[b], algo) for b in range(B)]}
+            pl, arena = self._pipe.enqueue_many(seeds, fan_out, replace, rng_seeds, slot=slot)
+            sampled = torch.cuda.Event()
+            sampled.record()
+            es, base = pl["es"], arena.data_ptr()
+            counts_ptr = base + B * pl["total"] * es
+            n_max = pl["ubs"][-1] + pl["nnz_ubs"][-1]
+            seen = pl.get("front_seen", 0)
+            n_ub = n_max if seen == 0 else min(n_max, seen + seen // 4 + 1024)
+            it = ID_DTYPES[seeds.dtype]
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(self._xstream):
+                self._xstream.wait_event(sampled)
+                x_all = torch.empty((B, n_ub) + self._tail, dtype=self._dtype, device=self._device)
+                x_stride = n_ub * self._row_bytes
+                for b in range(B):
+                    front_ptr = base + (b * pl["total"] + pl["offs"][-1][0]) * es
+                    nf_dev = counts_ptr + 8 * (b * 2 * L + 2 * L - 1)
+                    self._extract_dyn(it, front_ptr, n_ub, nf_dev, x_all.data_ptr() + b * x_stride, algo)
+                y_all = None
+                if self._labels is not None:
+                    y_all = ops._CAPI_cuda_index_select(self._labels, seeds.reshape(-1)).reshape(
+                        (B, S) + tuple(self._labels.shape[1:]))
+                done = torch.cuda.Event()
+                done.record()
+            # memory handed across streams: keep the allocator from recycling it too early
+            arena.record_stream(self._xstream)
+            seeds.record_stream(self._xstream)
+            x_all.record_stream(main)
+            if y_all is not None:
+                y_all.record_stream(main)
+        return {"pl": pl, "arena": arena, "seeds": seeds, "x_all": x_all, "y_all": y_all, "done": done,
+                "n_ub": n_ub, "seen": seen, "slot": slot, "B": B, "L": L}
+
+    def _finish_group(self, h, algo):
+        if "fallback" in h:
+            return h["fallback"]
+        pl, arena, B, L, n_ub = h["pl"], h["arena"], h["B"], h["L"], h["n_ub"]
+        with _on_device(self._device):
+            self._pipe.wait_many(pl, arena, slot=h["slot"])
+            blocks_all = self._pipe._views_many(pl, arena, h["seeds"], slot=h["slot"])
+            counts = pl["counts2"][1] if h["slot"] else pl["counts_np"]
+            torch.cuda.current_stream().wait_event(h["done"])
+            out, big = [], 0
+            for b in range(B):
+                nf = int(counts[b * 2 * L + 2 * L - 1])
+                big = max(big, nf)
+                if nf > n_ub:       # the adaptive bound was too small for this batch
+                    fr = blocks_all[b][-1][1]
+                    x = (ops._CAPI_cuda_index_select(self._table, fr, algo) if self._fs is None
+                         else self._fs._CAPI_get_feature(fr, algo))
+                else:
+                    x = h["x_all"][b, :nf]
+                out.append((blocks_all[b], x, h["y_all"][b] if h["y_all"] is not None else None))
+            pl["front_seen"] = max(pl.get("front_seen", 0), big)
+        return out
 
     def load_many(self, seeds, fan_out, replace=False, rng_seeds=None, algo=0):
         """B mini-batches per call: seeds [B, S] (pinned host or CUDA) -> list of B

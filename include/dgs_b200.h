@@ -123,6 +123,9 @@ int dgs_loc_table_unpack(const void *table, int64_t capacity, int itype, void *k
  * of 3 (tools/extract_probe.py). */
 int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void *nids, int64_t n,
                      void *out, int algo, void *stream);
+/* Tuning knob (process-wide, default 8): resident CTAs per SM the gather kernels size their grid
+ * for.  Lower it when a gather shares the GPU with another kernel on a second stream. */
+int dgs_set_gather_ctas_per_sm(int ctas);
 /* cached gather: row i comes from peer shard feat[dev][idx] when nids[i] hits the location
  * table, else from host_table[nids[i]] (pinned / registered host memory, may be NULL when every
  * id is cached). */

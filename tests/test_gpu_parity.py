@@ -750,12 +750,14 @@ print(h.hexdigest())
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     digests = []
-    for mode in ("coop", "multi"):
-        env = dict(os.environ, DGS_BLOCKS_MODE=mode)
+    # coop: one cooperative launch per batch; split: one kernel per phase (what a big batch or B >= 2
+    # gets; forced here for B = 1); multi: the round-1 kernels, 3 launches per hop, 8-byte tables + wipes
+    for env_extra in ({"DGS_MB_SPLIT": "0"}, {"DGS_MB_SPLIT": "1"}, {"DGS_BLOCKS_MODE": "multi"}):
+        env = dict(os.environ, **env_extra)
         p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert p.returncode == 0, p.stderr[-2000:]
         digests.append(p.stdout.strip().splitlines()[-1])
-    assert digests[0] == digests[1]
+    assert digests[0] == digests[1] == digests[2]
 
 
 @pytest.mark.parametrize("replace", [False, True])
@@ -1084,6 +1086,30 @@ def test_build_blocks_csc(dgs, cuda, idt):
         dgs.ops.coo_rows_to_indptr(torch.tensor([3, 1], dtype=idt, device=cuda), 4, check_sorted=True)
     with pytest.raises(RuntimeError, match="ascending"):
         dgs.ops.coo_rows_to_indptr(torch.tensor([1, 4], dtype=idt, device=cuda), 4, check_sorted=True)
+
+
+def test_batch_loader_iter_many_equals_load_many(dgs, cuda):
+    """BatchLoader.iter_many (two streams: the sampling of group g + 1 overlaps the extracts of
+    group g; double-buffered hop sizes) yields exactly what load_many returns group by group."""
+    N, D = 9000, 100
+    indptr, indices, _ = dgs_synth.make_csr(N, 200000, seed=46, classes=8)
+    feat = dgs_synth.feature_rows(torch.arange(N), D)
+    labels = (torch.arange(N) % 47).to(cuda)
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    loader = dgs.classes.BatchLoader(smp, feat.to(cuda), labels)
+    g = torch.Generator().manual_seed(9)
+    groups = [torch.randperm(N, generator=g)[:4 * 128].reshape(4, 128) for _ in range(7)]
+    src = [grp.pin_memory() if i % 2 else grp.to(cuda) for i, grp in enumerate(groups)]
+    rng = lambda gi: [1000 * gi + b for b in range(4)]
+    got = list(loader.iter_many(src, [10, 5], False, rng))
+    assert len(got) == 7
+    for gi, res in enumerate(got):
+        ref = loader.load_many(groups[gi].to(cuda), [10, 5], False, rng(gi))
+        assert len(res) == len(ref) == 4
+        for (blocks, x, y), (rb, rx, ry) in zip(res, ref):
+            assert all(torch.equal(u, v) for p_, q_ in zip(blocks, rb) for u, v in zip(p_, q_))
+            assert torch.equal(x, rx) and torch.equal(y, ry)
+            assert torch.equal(x.cpu(), feat[blocks[-1][1].cpu()])
 
 
 def test_guard_bands_stay_untouched(dgs, cuda):
