@@ -187,6 +187,19 @@ def main():
         ref = smp._CAPI_sample_node_classifiction(seeds, [10, 5], False, rng_seed=50 + it)
         assert all(torch.equal(a, b) for u, v in zip(blocks, ref) for a, b in zip(u, v))
         assert y is None and torch.equal(x.cpu(), feat[ref[-1][1].cpu()])
+    # B batches per sampling launch over the sharded sampler, sequential (load_many) and two-stream
+    # (iter_many, gathers capped at 2 CTAs per SM): both == single calls
+    grp = [torch.randperm(N, generator=torch.Generator().manual_seed(7 * rank + j))[:3 * 100].reshape(3, 100)
+           for j in range(4)]
+    rngf = lambda gi: [900 + 10 * gi + b for b in range(3)]
+    many = [loader.load_many(gq.pin_memory(), [10, 5], False, rngf(gi)) for gi, gq in enumerate(grp)]
+    piped = list(loader.iter_many([gq.to(dev) for gq in grp], [10, 5], False, rngf, 0, 2))
+    for gi in range(4):
+        for b in range(3):
+            ref = smp._CAPI_sample_node_classifiction(grp[gi][b].to(dev), [10, 5], False, rng_seed=rngf(gi)[b])
+            for res in (many[gi][b], piped[gi][b]):
+                assert all(torch.equal(a, c) for u, v in zip(res[0], ref) for a, c in zip(u, v))
+                assert torch.equal(res[1].cpu(), feat[ref[-1][1].cpu()])
     smp.close()
     dist.barrier()
     fsm.close()

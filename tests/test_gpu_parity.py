@@ -839,6 +839,29 @@ def test_sample_many_equals_single_calls(dgs, cuda, idt, bias, replace):
         assert all(torch.equal(u, v) for x, y in zip(many[b], one) for u, v in zip(x, y))
 
 
+def test_relabel_table_epoch_tags_wrap(dgs, cuda):
+    """The direct relabel tables are never wiped: entries carry an 8-bit epoch tag that counts down
+    per hop and the host clears the table when the tags run out (every 255 hops).  300 consecutive
+    calls on ONE workspace (3 hops each -> three wraps), alternating two seed sets so that stale
+    entries of the previous call are always in the table: every call must reproduce its reference."""
+    N = 6000
+    indptr, indices, _ = dgs_synth.make_csr(N, 150000, seed=81)
+    smp = dgs.classes.CSRSampler(indptr.to(cuda), indices.to(cuda))
+    g = torch.Generator().manual_seed(1)
+    sets = [torch.randint(0, N, (256,), generator=g).to(cuda) for _ in range(2)]
+    fan = [6, 5, 4]
+    ref = [smp._pipe._sample_per_hop(sd, fan, False, 40 + i) for i, sd in enumerate(sets)]
+    for it in range(300):
+        i = it & 1
+        out = smp._CAPI_sample_node_classifiction(sets[i], fan, False, rng_seed=40 + i)
+        assert all(torch.equal(u, v) for x, y in zip(out, ref[i]) for u, v in zip(x, y)), it
+    many = torch.stack(sets)
+    for it in range(100):
+        out = smp.sample_many(many, fan, False, [40, 41])
+        for i in range(2):
+            assert all(torch.equal(u, v) for x, y in zip(out[i], ref[i]) for u, v in zip(x, y)), it
+
+
 def test_sample_many_copy_path_matches_oracle(dgs, cuda):
     """All-neighbour fan-outs through the multi-batch kernel against the oracle's layer loop."""
     N = 1500
