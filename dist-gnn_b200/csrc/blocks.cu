@@ -1399,9 +1399,12 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
   }
 }
 
-// ---------------- epilogue: the hop sizes go straight into the caller's pinned host memory (posted
-// PCIe writes): entry 0 is written last, behind a system-scope fence, and is what the host polls.
-// (All sizes are final once the last hop's rank phase is over; other CTAs may still be emitting.)
+// ---------------- the hop sizes go straight into the caller's pinned host memory (posted PCIe
+// writes): entry 0 is written last, behind a system-scope fence, and is what the host polls.
+// All sizes are final once the last hop's rank phase is over, so they are delivered BEFORE the last
+// emit phase: the host builds its views and enqueues the next kernel (the extract, ordered behind
+// this one on the stream) while the last hop is still being written - ~9 us of host latency hidden
+// per batch.
 __device__ __forceinline__ void mb_deliver_counts(const MbArgs &a) {
   if (a.host_counts != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     const int n = 2 * a.L * a.B;
@@ -1437,12 +1440,12 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
     stamp();
     grid.sync();
     stamp();
+    if (l + 1 == a.L) mb_deliver_counts(a);
     mb_emit<IdT, kEmBatch>(ws0, a, l, sh, dyn_smem);
     stamp();
     if (l + 1 < a.L) grid.sync();   // (nothing follows the last emit)
     stamp();
   }
-  mb_deliver_counts(a);
 }
 
 // The same phases as separate kernels (B >= 2): a phase of B batches is throughput work, and a
@@ -1470,8 +1473,8 @@ __global__ void __launch_bounds__(kBkThreads, 4) mb_emit_kernel(BlocksWs ws0, Mb
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
-  mb_emit<IdT, 4>(ws0, a, l, sh, dyn_smem);
   if (l + 1 == a.L) mb_deliver_counts(a);
+  mb_emit<IdT, 4>(ws0, a, l, sh, dyn_smem);
 }
 
 __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {

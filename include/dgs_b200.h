@@ -235,9 +235,10 @@ int dgs_debug_ares_keys(const float *weights, int64_t deg, uint64_t rng_key, uin
  * counts have arrived there - the single host round trip of a batch.  If the memory is mapped
  * into the device's address space (cudaHostAlloc / cudaHostRegister under UVA) the cooperative
  * kernel writes the counts itself and the host polls for them (no copy engine, no stream
- * synchronisation; the kernel may still be retiring when the call returns - later work on the
- * same stream is ordered behind it as usual); otherwise they are copied and the stream is
- * synchronised. */
+ * synchronisation; the kernel is still writing the last hop's outputs when the call returns - the
+ * sizes are final before that phase - so later work on the same stream is ordered behind it as
+ * usual and anything else must synchronise with the stream); otherwise they are copied and the
+ * stream is synchronised. */
 int64_t dgs_sample_blocks_ws_bytes(int itype, int64_t num_seeds, int num_layers,
                                    const int64_t *fan_out, int64_t num_nodes);
 int dgs_sample_blocks_ws_init(void *ws, int64_t ws_bytes, int itype, int64_t num_seeds,
