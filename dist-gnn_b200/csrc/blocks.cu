@@ -370,7 +370,10 @@ fused_pick_kernel(GraphSrc g, const IdT *__restrict__ seeds, int64_t S_ub,
 // earlier phase is read with ld.global.cg (L2), never through a possibly stale L1 line.
 constexpr int kPkSeeds = 128;  // seeds per pick tile (256 was slower on B200: 4 B2 rounds per tile)
 constexpr int kPkBatch = 4;    // padded slots per thread and pass in the pick phase (8: no gain)
-constexpr int kEmBatch = 4;    // padded slots per thread and pass in the emit phase (8 spills)
+#ifndef DGS_EM_BATCH
+#define DGS_EM_BATCH 4
+#endif
+constexpr int kEmBatch = DGS_EM_BATCH;    // padded slots per thread and pass in the emit phase
 constexpr int kRkItems = 8;    // padded slots per thread and pass in the rank phase
 constexpr int kHubDeg = 512;   // biased sampling: rows longer than this are scanned by the whole CTA (measured: 2048 slower)
 
@@ -1474,7 +1477,10 @@ __global__ void __launch_bounds__(kBkThreads, 4) mb_emit_kernel(BlocksWs ws0, Mb
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
   if (l + 1 == a.L) mb_deliver_counts(a);
-  mb_emit<IdT, 4>(ws0, a, l, sh, dyn_smem);
+#ifndef DGS_EM_BATCH_SPLIT
+#define DGS_EM_BATCH_SPLIT 4
+#endif
+  mb_emit<IdT, DGS_EM_BATCH_SPLIT>(ws0, a, l, sh, dyn_smem);
 }
 
 __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {

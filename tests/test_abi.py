@@ -71,6 +71,51 @@ def test_capacity_and_workspace_sizes():
         assert lib.dgs_extract_indptr_ws_bytes(n) >= 256
 
 
+def test_batch_workspace_planning_without_gpu():
+    """Host-only logic of the whole-batch sampler: which kernel path a workspace is laid out for,
+    how it scales with the batches per launch, and the registry check that refuses a workspace the
+    library has never initialised - no kernel is launched."""
+    from dgs import _lib
+    lib = _lib.lib()
+    fo = _lib.i64_array([15, 10, 5])
+    N = 2449029
+    one = lib.dgs_sample_blocks_multi_ws_bytes(1, 1, 1024, 3, fo, N)
+    assert one > 4 * N                                   # the 4-byte-per-node table + per-slot arrays
+    assert one == lib.dgs_sample_blocks_ws_bytes(1, 1024, 3, fo, N)     # B = 1 is the same layout
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 8, 1024, 3, fo, N) == 8 * one
+    assert lib.dgs_sample_blocks_multi_ws_bytes(0, 1, 1024, 3, fo, N) < one      # int32 ids: smaller slots
+    # no multi-batch path: unknown node count, fan-out 0, too many batches, items of a hop >= 2^24
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 1, 1024, 3, fo, 0) == -1
+    assert b"single-batch path" in lib.dgs_last_error()
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 1, 1024, 2, _lib.i64_array([5, 0]), N) == -1
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 17, 1024, 3, fo, N) == -1
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 1, 8192, 3, _lib.i64_array([20, 15, 10]), N) == -1
+    assert lib.dgs_sample_blocks_multi_ws_bytes(1, 1, 4096, 3, _lib.i64_array([20, 15, 10]), N) > 0   # friendster
+    # ... while the single-batch entry still sizes a (hashed / wiped-table) workspace for them
+    assert lib.dgs_sample_blocks_ws_bytes(1, 1024, 3, fo, 0) > 0
+    assert lib.dgs_sample_blocks_ws_bytes(1, 1024, 2, _lib.i64_array([5, 0]), N) > 0
+    # a workspace pointer the library never initialised is refused before anything is launched
+    before = lib.dgs_launch_count()
+    g = _lib.Graph()
+    g.itype = g.etype = 1
+    g.num_nodes = N
+    buf = (C.c_char * 64)()
+    arr = (C.c_void_p * 3)(1, 1, 1)
+    caps = _lib.i64_array([1 << 30] * 3)
+    rc = lib.dgs_sample_blocks(C.byref(g), C.addressof(buf), 1024, 3, fo, 0, C.c_uint64(1), arr, arr, arr, caps,
+                               caps, C.addressof(buf), C.addressof(buf), one, 0, None, None)
+    assert rc != 0 and b"never initialised" in lib.dgs_last_error()
+    rng = (C.c_uint64 * 2)(1, 2)
+    rc = lib.dgs_sample_blocks_multi(C.byref(g), 2, C.addressof(buf), 8192, 1024, 3, fo, 0, rng, arr, arr, arr, 0,
+                                     caps, caps, C.addressof(buf), C.addressof(buf), one, None, 0, None)
+    assert rc != 0 and b"never initialised" in lib.dgs_last_error()
+    rc = lib.dgs_load_batch(None, None, None, 0, None, 0, 0, None, 0, C.c_uint64(0), None, None, None, None, 0,
+                            None, 0, 0, None, None, 0, None, None, 0, None)
+    assert rc != 0 and b"null argument" in lib.dgs_last_error()
+    assert lib.dgs_set_gather_ctas_per_sm(0) != 0 and lib.dgs_set_gather_ctas_per_sm(8) == 0
+    assert lib.dgs_launch_count() == before
+
+
 def test_nccl_context_defaults():
     import dgs
     assert dgs.ops._Test_GetWorldSize() == 1
