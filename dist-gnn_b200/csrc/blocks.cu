@@ -1094,6 +1094,8 @@ struct MbHop {
 struct MbArgs {
   int L, B;
   unsigned int tag0;                  // hop l stores / expects tag (tag0 - l) in bits 31..24
+  int scan_in_emit;                   // B = 1 cooperative launch: no last-CTA tail in the rank phase,
+                                      // every CTA scans the tile totals itself after the barrier
   int64_t seeds_stride, out_stride, ws_stride;   // bytes between consecutive batches
   long long *counts_dev;              // [B][2 L]  {nnz_0, |frontier_0|, nnz_1, ...}
   long long *host_counts;             // same layout in mapped pinned host memory (or null)
@@ -1231,6 +1233,7 @@ __device__ __forceinline__ void mb_rank(const BlocksWs &ws0, const MbArgs &a, in
     for (int64_t tile = t0; tile < tiles; tile += G) {
       rank_one_tile<IdT, true>(tile, S_ub, S, k, cur, w, unique_seeds, seeds_b, (const IdT *)w.pad_col,
                                tagbits);
+      if (a.scan_in_emit) continue;   // (the grid barrier that follows publishes the tile totals)
       __threadfence();
       __syncthreads();
       if (tid == 0) sh.last = (atomicAdd(w.done, 1u) == (unsigned int)(tiles - 1));
@@ -1245,11 +1248,26 @@ __device__ __forceinline__ void mb_rank(const BlocksWs &ws0, const MbArgs &a, in
   }
 }
 
+// ---------------- the hop sizes go straight into the caller's pinned host memory (posted PCIe
+// writes): entry 0 is written last, behind a system-scope fence, and is what the host polls.
+// All sizes are final once the last hop's rank phase is over, so they are delivered BEFORE the last
+// emit phase: the host builds its views and enqueues the next kernel (the extract, ordered behind
+// this one on the stream) while the last hop is still being written - ~9 us of host latency hidden
+// per batch.
+__device__ __forceinline__ void mb_deliver_counts(const MbArgs &a) {
+  if (a.host_counts != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int n = 2 * a.L * a.B;
+    for (int i = 1; i < n; ++i) a.host_counts[i] = ldcg(a.counts_dev + i);
+    __threadfence_system();
+    *(volatile long long *)a.host_counts = ldcg(a.counts_dev);
+  }
+}
+
 // ---------------- emit over the concatenated seed / slot spaces of all batches.  EB = padded slots
 // per thread and pass (independent load chains in flight).
 template <typename IdT, int EB>
 __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, int l, MbShared &sh,
-                                        unsigned char *dyn_smem) {
+                                        unsigned char *dyn_smem, bool deliver) {
   const int B = a.B;
   const int tid = threadIdx.x;
   const int64_t G = gridDim.x;
@@ -1267,7 +1285,13 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
   // fit, so the three prefix lookups per slot never leave the SM
   unsigned int *sp = reinterpret_cast<unsigned int *>(dyn_smem);
   const int tiles_ub = (int)((S_ub + kBkTile - 1) / kBkTile + 1);   // entries per array
-  if (smem_pref) {
+  if (a.scan_in_emit) {
+    // B = 1, cooperative launch: ws.pref* hold the per-tile TOTALS; every CTA scans them into its own
+    // shared memory (no atomic counter, no serial tail CTA - measured 84 -> 80 us per batch in
+    // round 1) and CTA 0 publishes the hop sizes
+    scan_totals_to_smem(sh.S[0], ws0, unique_seeds, sp, sp + tiles_ub, sp + 2 * tiles_ub,
+                        a.counts_dev + 2 * l, a.counts_dev + 2 * l + 1);
+  } else if (smem_pref) {
     // one flat loop over (batch, tile): a loop over the batches would be B dependent round trips
     // (measured: the emit phase of a tiny hop took 19 us at B = 16 instead of 4)
     const int total = B * tiles_ub;
@@ -1298,6 +1322,7 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
     sh.off2[B] = o2;
   }
   __syncthreads();
+  if (deliver) mb_deliver_counts(a);    // all hop sizes are final here: hand them to the host now
   const int64_t stride = G * kBkThreads;
   const int64_t gtid = (int64_t)blockIdx.x * kBkThreads + tid;
   // seeds -> frontier
@@ -1402,21 +1427,6 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
   }
 }
 
-// ---------------- the hop sizes go straight into the caller's pinned host memory (posted PCIe
-// writes): entry 0 is written last, behind a system-scope fence, and is what the host polls.
-// All sizes are final once the last hop's rank phase is over, so they are delivered BEFORE the last
-// emit phase: the host builds its views and enqueues the next kernel (the extract, ordered behind
-// this one on the stream) while the last hop is still being written - ~9 us of host latency hidden
-// per batch.
-__device__ __forceinline__ void mb_deliver_counts(const MbArgs &a) {
-  if (a.host_counts != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int n = 2 * a.L * a.B;
-    for (int i = 1; i < n; ++i) a.host_counts[i] = ldcg(a.counts_dev + i);
-    __threadfence_system();
-    *(volatile long long *)a.host_counts = ldcg(a.counts_dev);
-  }
-}
-
 // One cooperative launch: all hops, phases separated by grid barriers (lowest latency; B = 1).
 template <typename IdT, typename ET, int MODE>
 __global__ void __launch_bounds__(kBkThreads, DGS_COOP_MIN_CTAS)
@@ -1443,8 +1453,7 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
     stamp();
     grid.sync();
     stamp();
-    if (l + 1 == a.L) mb_deliver_counts(a);
-    mb_emit<IdT, kEmBatch>(ws0, a, l, sh, dyn_smem);
+    mb_emit<IdT, kEmBatch>(ws0, a, l, sh, dyn_smem, l + 1 == a.L);
     stamp();
     if (l + 1 < a.L) grid.sync();   // (nothing follows the last emit)
     stamp();
@@ -1476,11 +1485,10 @@ __global__ void __launch_bounds__(kBkThreads, 4) mb_emit_kernel(BlocksWs ws0, Mb
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
-  if (l + 1 == a.L) mb_deliver_counts(a);
 #ifndef DGS_EM_BATCH_SPLIT
 #define DGS_EM_BATCH_SPLIT 4
 #endif
-  mb_emit<IdT, DGS_EM_BATCH_SPLIT>(ws0, a, l, sh, dyn_smem);
+  mb_emit<IdT, DGS_EM_BATCH_SPLIT>(ws0, a, l, sh, dyn_smem, l + 1 == a.L);
 }
 
 __global__ void blocks_ws_init_kernel(int4 *p, int64_t n16) {
@@ -1707,6 +1715,12 @@ static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t se
       DGS_LAUNCH_CHECK();
     }
     return 0;
+  }
+  {
+    static const bool no_scan = getenv("DGS_MB_TAIL") != nullptr;   // force the last-CTA tail (A/B runs)
+    bool all_pref = true;
+    for (int l = 0; l < L; ++l) all_pref = all_pref && a.hop[l].smem_pref;
+    a.scan_in_emit = (B == 1 && all_pref && !no_scan) ? 1 : 0;
   }
   void *kern = nullptr;
 #define DGS_MB(M) kern = (void *)multi_batch_kernel<IdT, ET, M>
