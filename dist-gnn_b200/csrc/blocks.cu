@@ -1152,6 +1152,7 @@ struct MbShared {
   long long S[DGS_MAX_BATCHES];          // live seed count of every batch, this hop
   long long off[DGS_MAX_BATCHES + 1];    // exclusive offsets (seeds)
   long long off2[DGS_MAX_BATCHES + 1];   // exclusive offsets (padded slots)
+  long long next_S;                      // scan_in_emit: |frontier| of this hop = seeds of the next one
   bool last;
 };
 
@@ -1291,6 +1292,10 @@ __device__ __forceinline__ void mb_emit(const BlocksWs &ws0, const MbArgs &a, in
     // round 1) and CTA 0 publishes the hop sizes
     scan_totals_to_smem(sh.S[0], ws0, unique_seeds, sp, sp + tiles_ub, sp + 2 * tiles_ub,
                         a.counts_dev + 2 * l, a.counts_dev + 2 * l + 1);
+    if (tid == 0) {   // every CTA knows the next hop's seed count without another global round trip
+      const int tl = (int)((sh.S[0] + kBkTile - 1) / kBkTile);
+      sh.next_S = (long long)sp[tl] + (long long)sp[tiles_ub + tl];
+    }
   } else if (smem_pref) {
     // one flat loop over (batch, tile): a loop over the batches would be B dependent round trips
     // (measured: the emit phase of a tiny hop took 19 us at B = 16 instead of 4)
@@ -1444,7 +1449,13 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
   };
   stamp();
   for (int l = 0; l < a.L; ++l) {
-    mb_load_S(a, l, sh);
+    if (a.scan_in_emit && l > 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) sh.S[0] = min((long long)a.hop[l].S_ub, sh.next_S);
+      __syncthreads();
+    } else {
+      mb_load_S(a, l, sh);
+    }
     mb_pick<IdT, ET, MODE>(g, ws0, a, l, sh);
     stamp();
     grid.sync();
