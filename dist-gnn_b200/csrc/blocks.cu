@@ -100,8 +100,30 @@ struct HopState {        // per-hop arrays that must survive until the next hop'
   unsigned int *lrank_at;  // [S_max + E_max]  rank inside its tile of the first occurrence at item x
 };
 
+// Weighted sampling: rows longer than kHubDeg weights ("hubs") that a pick tile defers to the
+// grid-wide hub phase of the multi-batch kernel (one entry per deferred seed).
+struct __align__(16) HubEnt {
+  const void *row;       // the seed's neighbour ids
+  const float *w;        // ... and weights
+  unsigned int i;        // seed index inside its batch
+  int deg;
+};
+constexpr int kHubChunk = 4096;     // weights per chunk = one 512-weight pass for each of the 8 warps
+constexpr int kHubMaxRows = 1024;   // rows / chunks / chunks per row the chunked hub phase handles
+constexpr int kHubMaxChunks = 4096; //   (beyond: one CTA per row, hub_rows)
+constexpr int kHubMaxPerRow = 32;
+struct HubList {
+  unsigned int *count;   // entries pushed this hop (reset at the start of the rank phase)
+  HubEnt *ent;           // [S_max]
+  unsigned int *done;    // [kHubMaxRows] chunks of row j finished (self-resetting)
+  float *ckey;           // [kHubMaxChunks][32] candidates of a chunk, best first
+  int *cidx;             // [kHubMaxChunks][32]
+  int *cnum;             // [kHubMaxChunks]
+};
+
 struct BlocksWs {
   unsigned int *done;
+  HubList hubs;
   long long *pending_S;              // live seed count of the hop whose table is still dirty
   long long *prefA, *prefB, *prefC;  // [tiles_max + 1]
   int *loff;                         // [S_max] exclusive edge offset of seed i inside its tile
@@ -445,7 +467,8 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
                                                 IdT *__restrict__ pad_col, const HopState &cur,
                                                 uint64_t cap_mask, int ts, int64_t tile0,
                                                 int64_t tstride, unsigned int tagbits,
-                                                unsigned long long *fine = nullptr) {
+                                                unsigned long long *fine = nullptr,
+                                                const HubList *hubs = nullptr) {
   extern __shared__ __align__(16) unsigned char pick_smem[];
   auto fstamp = [&](int slot) {
     if (fine != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -558,7 +581,23 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         if (lane == 0) nxt = atomicAdd(&s_next, 1);
         s_ = __shfl_sync(0xffffffffu, nxt, 0);
       }
-      if (hubs_shared) {
+      if (hubs_shared && hubs != nullptr) {
+        // multi-batch kernel: hub rows are not scanned here - a tile that happens to own a few of
+        // them would keep the whole grid waiting at the next barrier (measured: 9-30 us of a
+        // 106 us batch).  They go to a grid-wide list that ALL CTAs drain in the hub phase.
+        if (tid < ns) {
+          const int deg = s_deg[tid];
+          if (deg > kHubDeg && deg > k) {
+            const unsigned int at = atomicAdd(hubs->count, 1u);
+            HubEnt e;
+            e.row = s_row[tid];
+            e.w = s_w[tid];
+            e.i = (unsigned int)(i0 + tid);
+            e.deg = deg;
+            hubs->ent[at] = e;
+          }
+        }
+      } else if (hubs_shared) {
         for (int s_ = 0; s_ < ns; ++s_) {
           const int deg = s_deg[s_];
           if (deg <= kHubDeg || deg <= k) continue;   // block-uniform
@@ -601,7 +640,9 @@ __device__ __forceinline__ void pick_tile_phase(const GraphSrc &g, const IdT *__
         if (el < slots) {
           const int si = el / k;
           const int j = el - si * k;
-          if (j < s_cnt[si]) {
+          const bool deferred = MODE == kBias && k <= 32 && hubs != nullptr && s_deg[si] > kHubDeg &&
+                                s_deg[si] > k;   // its picks come from the hub phase
+          if (j < s_cnt[si] && !deferred) {
             const int deg = s_deg[si];
             unsigned int p;
             if (MODE == kUniformReplace)
@@ -1113,6 +1154,10 @@ __device__ __forceinline__ T *off_ptr(T *p, int64_t bo) {
 __device__ __forceinline__ Tab tab_of(const BlocksWs &w0, int64_t bo) {
   return Tab{w0.hop[0].table.base + bo, 2};
 }
+__device__ __forceinline__ HubList hubs_of_batch(const BlocksWs &w0, int64_t bo) {
+  return HubList{off_ptr(w0.hubs.count, bo), off_ptr(w0.hubs.ent, bo), off_ptr(w0.hubs.done, bo),
+                 off_ptr(w0.hubs.ckey, bo), off_ptr(w0.hubs.cidx, bo), off_ptr(w0.hubs.cnum, bo)};
+}
 __device__ __forceinline__ HopState hop_of_batch(const BlocksWs &w0, int64_t bo) {
   HopState h;
   h.cnt = off_ptr(w0.hop[0].cnt, bo);
@@ -1128,6 +1173,7 @@ constexpr unsigned int kItemMask = 0x00ffffffu;   // low 24 bits of `first`: the
 __device__ __forceinline__ BlocksWs ws_of_batch(const BlocksWs &w0, int64_t bo) {
   BlocksWs w;
   w.done = off_ptr(w0.done, bo);
+  w.hubs = hubs_of_batch(w0, bo);
   w.pending_S = nullptr;
   w.prefA = off_ptr(w0.prefA, bo);
   w.prefB = off_ptr(w0.prefB, bo);
@@ -1145,6 +1191,194 @@ __device__ __forceinline__ int batch_of(const long long *off, int B, long long v
   int b = 0;
   for (int i = 1; i < B; ++i) b += (v >= off[i]) ? 1 : 0;
   return b;
+}
+
+// Hub phase (weighted sampling without replacement, k <= 32): the deferred rows of every batch form
+// one list that is dealt round-robin to ALL CTAs.  A CTA scans a row with its 8 warps (every 8th
+// 512-weight pass each), ranks the finalists across warps and does the row's k neighbour loads +
+// table inserts - exactly what the tile phase does for a row it owns, so the sample is the same.
+template <typename IdT>
+__device__ __forceinline__ void hub_rows(const HubList &hubs, int64_t j0, int64_t jstride, int k,
+                                         uint64_t rng_key, int64_t S_ub, IdT *__restrict__ pad_col,
+                                         const Tab &table, unsigned int tagbits) {
+  __shared__ int h_mcount[kBkWarps];
+  __shared__ unsigned int h_pick[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = (int64_t)ldcg(hubs.count);
+  for (int64_t j = j0; j < n; j += jstride) {
+    const int4 raw0 = __ldcg(reinterpret_cast<const int4 *>(hubs.ent + j));
+    const int2 raw1 = __ldcg(reinterpret_cast<const int2 *>(hubs.ent + j) + 2);
+    const IdT *row = reinterpret_cast<const IdT *>(((unsigned long long)(unsigned int)raw0.y << 32) | (unsigned int)raw0.x);
+    const float *w = reinterpret_cast<const float *>(((unsigned long long)(unsigned int)raw0.w << 32) | (unsigned int)raw0.z);
+    const unsigned int i = (unsigned int)raw1.x;
+    const int deg = raw1.y;
+    __syncthreads();   // the candidate lists / picks of the previous row have been read
+    const AresBuf mine = ares_buf(warp);
+    const int M = ares_collect(w, deg, k, 512 * warp, 512 * kBkWarps, rng_key, (uint64_t)i, lane, mine);
+    if (lane == 0) h_mcount[warp] = M;
+    __syncthreads();
+    if (lane < M) {
+      const float kv = mine.key[lane];
+      const int iv = mine.idx[lane];
+      int rank = 0;
+      for (int ww = 0; ww < kBkWarps; ++ww) {
+        const AresBuf o = ares_buf(ww);
+        const int Mo = h_mcount[ww];
+        for (int q = 0; q < Mo; ++q) rank += ares_before(o.key[q], o.idx[q], kv, iv) ? 1 : 0;
+      }
+      if (rank < k) h_pick[rank] = (unsigned int)iv;
+    }
+    __syncthreads();
+    if (tid < k) {
+      const IdT v = row[h_pick[tid]];
+      const int64_t e = (int64_t)i * k + tid;
+      atomicMin(table.first((uint64_t)v), (unsigned int)(S_ub + e) | tagbits);
+      pad_col[e] = v;
+    }
+  }
+}
+
+// Chunked hub phase: a row of 17 000 weights on ONE CTA is ~15 us, longer than everything else in
+// the hop.  Rows are cut into chunks of kHubChunk weights; the (row, chunk) pairs of a batch are
+// dealt round-robin to the CTAs.  A chunk's CTA keeps the chunk's k best candidates (ordered); the
+// CTA that finishes a row's LAST chunk merges the row's candidates (every candidate counts how
+// many beat it - the total order is (key descending, position ascending), so set and order equal
+// the single-CTA and single-warp selections) and does the row's neighbour loads + table inserts.
+// Returns false (nothing done) when the list exceeds the static limits: the caller then runs
+// hub_rows.  q0 / qstride: the chunk ids this CTA owns.
+template <typename IdT>
+__device__ __forceinline__ bool hub_chunks(const HubList &hubs, int64_t rot, int k, uint64_t rng_key,
+                                           int64_t S_ub, IdT *__restrict__ pad_col, const Tab &table,
+                                           unsigned int tagbits, long long *total_chunks) {
+  __shared__ int c_qoff[kHubMaxRows + 1];      // exclusive chunk offsets of the rows
+  __shared__ long long c_scan[32];
+  __shared__ long long c_total;
+  __shared__ int c_mcount[kBkWarps];
+  __shared__ float m_key[kHubMaxPerRow * 32];  // merge: candidates of all chunks of one row
+  __shared__ int m_idx[kHubMaxPerRow * 32];
+  __shared__ int m_n;
+  __shared__ unsigned int c_pick[32];
+  __shared__ bool c_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int n = (int)ldcg(hubs.count);
+  *total_chunks = 0;
+  if (n == 0) return true;
+  if (n > kHubMaxRows) return false;
+  // chunks per row -> exclusive offsets (4 rows per thread)
+  __syncthreads();
+  int nch[4], mine = 0;
+  bool too_long = false;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tid * 4 + u;
+    nch[u] = 0;
+    if (j < n) {
+      const int deg = __ldcg(reinterpret_cast<const int *>(hubs.ent + j) + 5);
+      nch[u] = (deg + kHubChunk - 1) / kHubChunk;
+      too_long |= nch[u] > kHubMaxPerRow;
+    }
+    mine += nch[u];
+  }
+  long long ex = block_exclusive_scan<long long>((long long)mine, c_scan, &c_total);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tid * 4 + u;
+    if (j <= n && j <= kHubMaxRows) c_qoff[min(j, kHubMaxRows)] = (int)ex;
+    ex += nch[u];
+  }
+  const bool bad = __syncthreads_or(too_long ? 1 : 0) != 0;
+  const int Q = (int)c_total;
+  if (bad || Q > kHubMaxChunks) return false;
+  if (tid == 0) c_qoff[n] = Q;
+  __syncthreads();
+  *total_chunks = Q;
+  for (int q = (int)(((int64_t)blockIdx.x - rot) % G + G) % G; q < Q; q += G) {
+    // row of chunk q: last j with c_qoff[j] <= q (binary search, uniform)
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (c_qoff[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int j = lo, c = q - c_qoff[j], nchunks = c_qoff[j + 1] - c_qoff[j];
+    const int4 raw0 = __ldcg(reinterpret_cast<const int4 *>(hubs.ent + j));
+    const int2 raw1 = __ldcg(reinterpret_cast<const int2 *>(hubs.ent + j) + 2);
+    const IdT *row = reinterpret_cast<const IdT *>(((unsigned long long)(unsigned int)raw0.y << 32) | (unsigned int)raw0.x);
+    const float *w = reinterpret_cast<const float *>(((unsigned long long)(unsigned int)raw0.w << 32) | (unsigned int)raw0.z);
+    const unsigned int i = (unsigned int)raw1.x;
+    const int deg = raw1.y;
+    const int c_end = min(deg, (c + 1) * kHubChunk);
+    __syncthreads();   // shared buffers of the previous chunk have been read
+    const AresBuf mine_b = ares_buf(warp);
+    const int M = ares_collect(w, c_end, k, c * kHubChunk + 512 * warp, kHubChunk, rng_key, (uint64_t)i, lane,
+                               mine_b);
+    if (lane == 0) c_mcount[warp] = M;
+    __syncthreads();
+    // the chunk's k best, in order, to shared memory (single chunk) or to the row's global slots
+    if (lane < M) {
+      const float kv = mine_b.key[lane];
+      const int iv = mine_b.idx[lane];
+      int rank = 0;
+      for (int ww = 0; ww < kBkWarps; ++ww) {
+        const AresBuf o = ares_buf(ww);
+        const int Mo = c_mcount[ww];
+        for (int t = 0; t < Mo; ++t) rank += ares_before(o.key[t], o.idx[t], kv, iv) ? 1 : 0;
+      }
+      if (rank < k) {
+        if (nchunks == 1) {
+          c_pick[rank] = (unsigned int)iv;
+        } else {
+          hubs.ckey[(size_t)q * 32 + rank] = kv;
+          hubs.cidx[(size_t)q * 32 + rank] = iv;
+        }
+      }
+    }
+    if (nchunks > 1) {
+      if (tid == 0) {
+        int tot = 0;
+        for (int ww = 0; ww < kBkWarps; ++ww) tot += c_mcount[ww];
+        hubs.cnum[q] = min(tot, k);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) c_last = atomicAdd(hubs.done + j, 1u) == (unsigned int)(nchunks - 1);
+      __syncthreads();
+      if (!c_last) continue;            // (uniform) another CTA will merge this row
+      __threadfence();
+      if (tid == 0) hubs.done[j] = 0;   // last user: leave the counter clean for the next hop
+      // gather the row's candidates: chunk c2 contributes cnum entries
+      const int q0 = c_qoff[j];
+      if (tid == 0) m_n = 0;
+      __syncthreads();
+      for (int c2 = warp; c2 < nchunks; c2 += kBkWarps) {
+        const int cn = __ldcg(hubs.cnum + q0 + c2);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&m_n, cn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < cn) {
+          m_key[base + lane] = __ldcg(hubs.ckey + (size_t)(q0 + c2) * 32 + lane);
+          m_idx[base + lane] = __ldcg(hubs.cidx + (size_t)(q0 + c2) * 32 + lane);
+        }
+      }
+      __syncthreads();
+      const int T = m_n;
+      for (int t = tid; t < T; t += kBkThreads) {
+        const float kv = m_key[t];
+        const int iv = m_idx[t];
+        int rank = 0;
+        for (int o = 0; o < T; ++o) rank += ares_before(m_key[o], m_idx[o], kv, iv) ? 1 : 0;
+        if (rank < k) c_pick[rank] = (unsigned int)iv;
+      }
+    }
+    __syncthreads();
+    if (tid < k) {
+      const IdT v = row[c_pick[tid]];
+      const int64_t e = (int64_t)i * k + tid;
+      atomicMin(table.first((uint64_t)v), (unsigned int)(S_ub + e) | tagbits);
+      pad_col[e] = v;
+    }
+  }
+  return true;
 }
 
 // Shared-memory scratch of the multi-batch phases.
@@ -1199,11 +1433,45 @@ __device__ __forceinline__ void mb_pick(const GraphSrc &g, const BlocksWs &ws0, 
     if (t0 >= tiles) continue;
     const int64_t bo = (int64_t)b * a.ws_stride;
     const HopState cur = hop_of_batch(ws0, bo);
+    const HubList hl = hubs_of_batch(ws0, bo);
     const uint64_t key = a.rng[b] + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
     pick_tile_phase<IdT, ET, MODE, true, FR>(
         g, off_ptr(seeds0, (int64_t)b * in_stride), S_ub, S, k, key,
         reinterpret_cast<IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo)), cur, 0, ts, t0, G,
-        tagbits);
+        tagbits, nullptr, (MODE == kBias && k <= 32) ? &hl : nullptr);
+  }
+}
+
+// does hop l of this launch have a hub phase?  (weighted, without replacement, k <= 32)
+template <int MODE>
+__device__ __forceinline__ bool mb_has_hubs(const MbArgs &a, int l) {
+  return MODE == kBias && a.hop[l].k <= 32;
+}
+
+// ---------------- hub phase: the deferred long rows of all batches, dealt round-robin to the CTAs
+template <typename IdT>
+__device__ __forceinline__ void mb_hubs(const BlocksWs &ws0, const MbArgs &a, int l) {
+  const int B = a.B;
+  const int64_t G = gridDim.x;
+  const int k = a.hop[l].k;
+  const unsigned int tagbits = (a.tag0 - (unsigned int)l) << 24;
+  long long off = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t bo = (int64_t)b * a.ws_stride;
+    const HubList hl = hubs_of_batch(ws0, bo);
+    const uint64_t key = a.rng[b] + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1);
+    IdT *pad = reinterpret_cast<IdT *>(off_ptr(reinterpret_cast<char *>(ws0.pad_col), bo));
+    long long chunks = 0;
+    if (hub_chunks<IdT>(hl, off, k, key, a.hop[l].S_ub, pad, tab_of(ws0, bo), tagbits, &chunks)) {
+      off += chunks;
+      continue;
+    }
+    // too many / too long rows for the chunk scratch: one CTA per row
+    const long long n = (long long)ldcg(hl.count);
+    const int64_t j0 = (((int64_t)blockIdx.x - off) % G + G) % G;
+    off += n;
+    if (j0 >= n) continue;
+    hub_rows<IdT>(hl, j0, G, k, key, a.hop[l].S_ub, pad, tab_of(ws0, bo), tagbits);
   }
 }
 
@@ -1220,6 +1488,7 @@ __device__ __forceinline__ void mb_rank(const BlocksWs &ws0, const MbArgs &a, in
   const int64_t in_stride = l == 0 ? a.seeds_stride : a.out_stride;
   const bool unique_seeds = l > 0;
   const unsigned int tagbits = (a.tag0 - (unsigned int)l) << 24;
+  if (blockIdx.x == 0 && tid < B) *off_ptr(ws0.hubs.count, (int64_t)tid * a.ws_stride) = 0;   // next hop's list
   long long toff = 0;
   for (int b = 0; b < B; ++b) {
     const int64_t S = sh.S[b];
@@ -1457,6 +1726,10 @@ multi_batch_kernel(GraphSrc g, BlocksWs ws0, MbArgs a) {
       mb_load_S(a, l, sh);
     }
     mb_pick<IdT, ET, MODE>(g, ws0, a, l, sh);
+    if (mb_has_hubs<MODE>(a, l)) {   // (one more barrier, weighted mode only)
+      grid.sync();
+      mb_hubs<IdT>(ws0, a, l);
+    }
     stamp();
     grid.sync();
     stamp();
@@ -1484,6 +1757,10 @@ mb_pick_kernel(GraphSrc g, BlocksWs ws0, MbArgs a, int l) {
   __shared__ MbShared sh;
   mb_load_S(a, l, sh);
   mb_pick<IdT, ET, MODE, FR>(g, ws0, a, l, sh);
+}
+template <typename IdT>
+__global__ void __launch_bounds__(kBkThreads, 4) mb_hub_kernel(BlocksWs ws0, MbArgs a, int l) {
+  mb_hubs<IdT>(ws0, a, l);
 }
 template <typename IdT>
 __global__ void __launch_bounds__(kBkThreads, 4) mb_rank_kernel(BlocksWs ws0, MbArgs a, int l) {
@@ -1602,12 +1879,21 @@ static int multi_plan(int itype, int B, int64_t num_seeds, int L, const int64_t 
   char *loff = take(S_max * 4);
   char *pad = take(E_max * idb);
   char *fslot = take(E_max * 4), *fseed = take(S_max * 4), *lrank_at = take((S_max + E_max) * 4);
+  char *hub_ent = take(S_max * (int64_t)sizeof(HubEnt));
+  char *hub_done = take(kHubMaxRows * 4), *hub_ckey = take((int64_t)kHubMaxChunks * 32 * 4),
+       *hub_cidx = take((int64_t)kHubMaxChunks * 32 * 4), *hub_cnum = take(kHubMaxChunks * 4);
   char *t0 = take(p->table_bytes);
   p->stride = off;
   p->bytes = off * B;
   if (ws) {
     memset(ws, 0, sizeof(*ws));
     ws->done = (unsigned int *)done;
+    ws->hubs.count = (unsigned int *)(done + 128);
+    ws->hubs.ent = (HubEnt *)hub_ent;
+    ws->hubs.done = (unsigned int *)hub_done;
+    ws->hubs.ckey = (float *)hub_ckey;
+    ws->hubs.cidx = (int *)hub_cidx;
+    ws->hubs.cnum = (int *)hub_cnum;
     ws->pending_S = (long long *)(done + 64);
     ws->prefA = (long long *)pa;
     ws->prefB = (long long *)pb;
@@ -1716,6 +2002,10 @@ static int launch_multi(const GraphSrc &src, int B, const IdT *seeds, int64_t se
 #undef DGS_MBP
 #undef DGS_MBP_
       DGS_LAUNCH_CHECK();
+      if (mode == kBias && k <= 32) {   // the long rows the pick tiles deferred
+        mb_hub_kernel<IdT><<<sms * 4, kBkThreads, 0, st>>>(ws, a, l);
+        DGS_LAUNCH_CHECK();
+      }
       const int64_t tiles = (int64_t)B * ((S_ub + kBkTile - 1) / kBkTile);
       mb_rank_kernel<IdT><<<(int)std::min<int64_t>(tiles, (int64_t)sms * 4), kBkThreads, 0, st>>>(ws, a, l);
       DGS_LAUNCH_CHECK();
@@ -2104,6 +2394,7 @@ extern "C" int dgs_sample_blocks_multi_ws_init(void *ws, int64_t ws_bytes, int i
   for (int b = 0; b < num_batches; ++b) {
     char *base = (char *)ws + (int64_t)b * p.stride;
     DGS_CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
+    DGS_CUDA_OK(cudaMemsetAsync((char *)w.hubs.done + (int64_t)b * p.stride, 0, kHubMaxRows * 4, st));
     DGS_CUDA_OK(cudaMemsetAsync(w.hop[0].table.base + (int64_t)b * p.stride, 0xFF, (size_t)p.table_bytes, st));
   }
   ws_register(ws, kPathMulti, itype, num_batches, num_seeds, num_layers, fan_out, num_nodes, p.bytes);
