@@ -21,9 +21,13 @@ def main():
     ap.add_argument("--rows", default="192000,1000000")
     ap.add_argument("--table-rows", type=int, default=2_449_029)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--l2gran", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32/64/128); 0 = leave")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    if args.l2gran:
+        from dgs import _lib
+        _lib.check(_lib.lib().dgs_set_l2_fetch_granularity(args.l2gran))
     peak = 6535.4
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
