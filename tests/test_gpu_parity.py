@@ -536,6 +536,49 @@ def test_biased_without_replacement_exact_topk(dgs, cuda, k):
         cur = f
 
 
+@pytest.mark.parametrize("case", ["many_hubs", "huge_row"])
+def test_biased_hub_phase_fallbacks_exact(dgs, cuda, case):
+    """The chunked hub phase of the batch kernel has static limits (1024 deferred rows, 32 chunks of
+    4096 weights per row); beyond them the rows are scanned one CTA per row.  Both fallbacks must
+    return exactly the top-k of the A-Res keys: (a) 2 000 seeds that are all > 512-weight rows,
+    (b) one row of 140 000 weights (35 chunks) next to ordinary ones."""
+    g = torch.Generator().manual_seed(5)
+    if case == "many_hubs":
+        N = 3000
+        deg = torch.full((N,), 600, dtype=torch.int64)
+        seeds = torch.randperm(N, generator=g)[:2000]
+    else:
+        N = 150000
+        deg = torch.randint(3, 9, (N,), generator=g)
+        deg[7] = 140000
+        deg[9] = 70000
+        seeds = torch.cat([torch.tensor([7, 9]), torch.randperm(N - 10, generator=g)[:300] + 10])
+        seeds = seeds[torch.randperm(seeds.numel(), generator=g)]
+    indptr = torch.zeros(N + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(deg, 0)
+    owner = torch.repeat_interleave(torch.arange(N), deg)
+    t = torch.arange(int(indptr[-1])) - indptr[owner]
+    indices = (owner * 1009 + t) % N
+    w = (torch.randn(indices.numel(), generator=g).abs() + 1e-3).float()
+    ip, ix, wd = indptr.to(cuda), indices.to(cuda), w.to(cuda)
+    smp = dgs.classes.CSRSampler(ip, ix, wd)
+    k, R = 25, 4242
+    (s_, f_, r_, c_), = smp._pipe.sample(seeds.to(cuda), [k], False, R)
+    cnt = torch.clamp(indptr[seeds + 1] - indptr[seeds], max=k)
+    assert torch.equal(r_.cpu(), torch.repeat_interleave(torch.arange(seeds.numel()), cnt))
+    per_seed = torch.split(f_.cpu()[c_.cpu()], cnt.tolist())
+    key = (R + GOLDEN) & M64
+    check = range(seeds.numel()) if case == "huge_row" else range(0, seeds.numel(), 41)
+    for i in check:
+        nid = int(seeds[i])
+        d = int(indptr[nid + 1] - indptr[nid])
+        pos = (per_seed[i] - nid * 1009) % N
+        if d <= k:
+            assert pos.tolist() == list(range(d))
+        else:
+            assert pos.tolist() == _expected_ares(dgs, wd, indptr, nid, k, key, i).tolist(), (case, nid, d)
+
+
 def test_biased_k1_and_replace_follow_weights_long_row(dgs, cuda):
     """deg 2 000 (four 512-weight passes per row): k = 1 w/o replacement and k = 7 with replacement
     must follow w_i / sum(w); chi-square over 2 000 cells, 6-sigma bound.  Through the per-hop op and
