@@ -770,6 +770,42 @@ def test_fused_blocks_edge_cases(dgs, cuda, idt):
         cur = f
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+def test_fused_blocks_small_first_hop(dgs, cuda, idt):
+    """Small first hops (<= 1024 seeds, fan-out <= 16, two to four hops) through the whole-batch
+    kernel.  Copy path against the oracle's layer loop on a graph whose rows are all <= 12 long
+    (isolated nodes, duplicate seeds, seed counts around the 8-seed pick tiles, the 128-seed rank
+    tiles and 1024), random path against the per-hop ops with the same Philox counters.  (Written
+    for the one-CTA first hop that round 2 measured and dropped - DESIGN.md section 5 - and kept:
+    it pins the tile phases on the same boundaries.)"""
+    N = 3000
+    g = torch.Generator().manual_seed(23)
+    deg = torch.randint(0, 13, (N,), generator=g)
+    deg[::7] = 0
+    indptr = torch.zeros(N + 1, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    indices = torch.randint(0, N, (int(indptr[-1]),), generator=g).to(idt)
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda))
+    for n_seeds in (1, 3, 4, 5, 255, 257, 1023, 1024, 1025):
+        seeds = torch.randint(0, N, (n_seeds,), generator=g).to(idt)           # duplicates allowed
+        for fan in ([12, 12], [16, 12, 12]):
+            exp = oracle.sample_blocks_all_neighbors(t2n(seeds), t2n(indptr), t2n(indices), len(fan))
+            out = smp._CAPI_sample_node_classifiction(seeds.to(cuda), fan, False)
+            for a, e in zip(out, exp):
+                for x, z in zip(a, e):
+                    assert x.dtype == idt and np.array_equal(t2n(x), z)
+    # random path: degrees on both sides of the fan-out, hubs, duplicates
+    indptr, indices, _ = dgs_synth.make_csr(9000, 400000, seed=29, id_dtype=idt)
+    smp = dgs.classes.CSRSampler(indptr.to(idt).to(cuda), indices.to(cuda))
+    for it, n_seeds in enumerate((2, 130, 777, 1024)):
+        seeds = torch.randint(0, 9000, (n_seeds,), generator=g).to(idt).to(cuda)
+        for fan in ([10, 5], [15, 10, 5], [4, 16], [3, 2, 1, 7]):
+            a = smp._pipe.sample(seeds, fan, False, 900 + it)
+            b = smp._pipe._sample_per_hop(seeds, fan, False, 900 + it)
+            assert len(a) == len(b) == len(fan)
+            assert all(torch.equal(u, v) for x, y in zip(a, b) for u, v in zip(x, y)), (n_seeds, fan)
+
+
 def test_fused_blocks_cooperative_equals_multi_kernel(dgs, cuda, monkeypatch):
     """The cooperative single-launch kernel and the 3-kernels-per-hop path share their phase code
     and RNG counters: identical outputs for the same seed (DGS_BLOCKS_MODE is read once per
