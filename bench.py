@@ -83,6 +83,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-extra-layout", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true",
+                    help="N > 1: skip the NCCL id-exchange variant in the extract-only leg")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 4096 if args.shape == "friendster" else 1024
@@ -723,10 +725,36 @@ def run_b200(args, fan_out):
         x1.record()
         barrier()
         xo_ms = reduce(x0.elapsed_time(x1), "max") / 6
-        del outs, qs
+        del outs
         payload = R * row_bytes * (world - 1) / world / (xo_ms * 1e-3) / 1e9
         extract_only = {"rows_per_gpu": R, "ms": xo_ms, "peer_payload_gbps_per_gpu": payload,
                         "algorithmic_gbps_per_gpu": R * (2 * row_bytes + 8) / (xo_ms * 1e-3) / 1e9}
+        # the north star's alternative, measured on the same requests: the ids travel to the owners
+        # over NCCL (all-to-all), the owners gather from their own shard, a second all-to-all brings
+        # the rows back (P2PCacheFeatureServer.get_feature_exchange) - against in-kernel peer loads
+        if getattr(feature_source, "_mod_world", -1) > 0 and hasattr(feature_source, "get_feature_exchange") \
+                and not args.no_exchange:
+            ex = feature_source.get_feature_exchange(qs[0])
+            same = torch.equal(ex, extract(qs[0]))
+            assert reduce(1.0 if same else 0.0, "min") == 1.0, "id-exchange extract differs from the peer-load extract"
+            del ex
+            feature_source.get_feature_exchange(qs[1])
+            barrier()
+            x0.record()
+            for i in range(4):
+                keep = feature_source.get_feature_exchange(qs[i % 2])
+            x1.record()
+            barrier()
+            ex_ms = reduce(x0.elapsed_time(x1), "max") / 4
+            del keep
+            extract_only.update({
+                "exchange_ms": ex_ms,
+                "exchange_payload_gbps_per_gpu": R * row_bytes * (world - 1) / world / (ex_ms * 1e-3) / 1e9,
+                "exchange_vs_peer_loads": xo_ms / ex_ms,
+                "exchange_what": "route kernel + all_gather(counts) + host read + NCCL all-to-all(ids) + "
+                                 "local gather + NCCL all-to-all(rows) + gather back to request order; "
+                                 "rows equal to the peer-load extract (asserted)"})
+        del qs
     clk = clocks.stop() if rank == 0 else None   # sampled from the warm-up through the timed regions
 
     # ---- N > 1, sharded headline: the full-replica layout (what the cache policy picks when

@@ -83,6 +83,8 @@ SIGNATURES = {
     "dgs_extract_p2p": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp,
                                   C.c_int, c_vp]),
     "dgs_extract_sharded": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
+    "dgs_route_ws_bytes": (c_i64, [c_i64, C.c_int]),
+    "dgs_route_ids": (C.c_int, [C.c_int, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dgs_extract_dyn": (C.c_int, [c_vp, c_vp, c_vp, c_i64, C.c_int, c_i64, C.c_int, c_vp, c_i64, c_vp,
                                   c_vp, C.c_int, c_vp]),
     "dgs_coo_rows_to_indptr": (C.c_int, [C.c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),

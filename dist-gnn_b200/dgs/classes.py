@@ -806,6 +806,21 @@ class P2PCacheFeatureServer:
                                             stream()), "_CAPI_get_feature")
         return out
 
+    def get_feature_exchange(self, nids, group=None):
+        """Extension (north star (4)): the same rows as _CAPI_get_feature, but the ids
+        travel to the owners over NCCL (all-to-all), the owners gather from their own shard and a
+        second all-to-all returns the rows - instead of in-kernel NVLink peer loads.  Modulo layout
+        only (every node cached, node n on rank n % world); collective over the torch.distributed
+        `group` whose ranks are the NCCL ranks of this server.  DistGNN.dist.exchange_extract."""
+        check_cuda(nids, "nids")
+        if self._mod_world <= 0:
+            raise RuntimeError("get_feature_exchange needs the modulo-sharded layout "
+                               "(cache_nids = arange(rank, N, world) on every rank)")
+        from DistGNN.dist import exchange_extract
+        local = self._CAPI_get_gpu_feature().reshape(-1, self._stride)
+        with torch.cuda.device(self._device):
+            return exchange_extract(nids, self._mod_world, self.device_id_, local, group=group)
+
     def _CAPI_get_local_cache_hashmap_tensors(self):
         """Extension (tests): the (key, idx, devid) view of the location table."""
         with torch.cuda.device(self._device):

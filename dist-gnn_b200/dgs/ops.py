@@ -111,6 +111,31 @@ def _CAPI_cuda_index_select(data, nids, algo=0):
     return out
 
 
+def route_ids(nids, world):
+    """Extension (north star (4): NCCL for the seed / ID exchange; no reference counterpart):
+    partition the requested node ids by owner for ONE all-to-all.  Node n lives on GPU n mod world
+    at slot n // world (the layout of the modulo-sharded extract).  Returns (send_idx, inv, counts):
+    send_idx = slot numbers grouped by owner, inv[i] = position of request i in that grouped order
+    (rows that come back in send order are put in request order by out = rows[inv]), counts =
+    int64[world] on the device.  Enqueued on the current stream, no host round trip."""
+    check_cuda(nids, "nids")
+    nids = nids.contiguous()
+    n = nids.numel()
+    l = lib()
+    it = itype(nids, "nids")
+    wsb = l.dgs_route_ws_bytes(n, int(world))
+    if wsb < 0:
+        raise RuntimeError(f"route_ids: world {world} not supported")
+    with torch.cuda.device(nids.device):
+        ws = torch.empty(int(wsb), dtype=torch.uint8, device=nids.device)
+        send_idx = torch.empty_like(nids)
+        inv = torch.empty_like(nids)
+        counts = torch.empty(int(world), dtype=torch.int64, device=nids.device)
+        check(l.dgs_route_ids(it, ptr(nids), n, int(world), ptr(send_idx), ptr(inv), ptr(counts),
+                              ptr(ws), wsb, stream()), "route_ids")
+    return send_idx, inv, counts
+
+
 # ------------------------------------------------------------------ sub-CSR extraction (test hooks)
 def _Test_ExtractIndptr(nids, indptr):
     """ExtractIndptr (src/sampling/cuda/utils.cu:12-42)."""

@@ -137,6 +137,16 @@ int dgs_extract_p2p(const dgs_p2p_server_t *feat, const void *host_table, int64_
 int dgs_extract_sharded(const dgs_p2p_server_t *feat, int64_t row_bytes, int itype,
                         const void *nids, int64_t n, void *out, int algo, void *stream);
 
+/* request routing for the id-exchange variant of the sharded extract (extension; north star (4)
+ * "NCCL used only for seed/ID exchange", SURVEY 8e "optional alternative to be measured against
+ * pure peer loads"; closest reference code: the build-time all-gather-v of id lists,
+ * src/nccl/nccl_context.cc:65-112).  Partitions n requested ids by owner (n mod world): send_idx =
+ * the owners' slot numbers (n / world) grouped by owner, inv[i] = position of request i in that
+ * grouped order, counts_dev[world] (int64, device) = requests per owner.  ws: dgs_route_ws_bytes. */
+int64_t dgs_route_ws_bytes(int64_t n, int world);
+int dgs_route_ids(int itype, const void *nids, int64_t n, int world, void *send_idx, void *inv,
+                  int64_t *counts_dev, void *ws, int64_t ws_bytes, void *stream);
+
 /* gather with a device-side row count (extension): n_dev (device int64) holds the live
  * number of rows, n_ub bounds the grid and the capacity of `out` - the extract of a mini-batch can
  * be enqueued right behind dgs_sample_blocks, before the host knows the frontier size.

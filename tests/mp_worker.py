@@ -179,6 +179,15 @@ def main():
     assert fsm._mod_world == world
     for algo in (0, 1, 2):
         assert torch.equal(fsm._CAPI_get_feature(q, algo).cpu(), feat[q.cpu()])
+    # id-exchange variant (NCCL all-to-all of ids, owners gather locally, rows come back): same rows,
+    # for request counts that differ per rank, an empty request and ids that all have one owner
+    gq = torch.Generator().manual_seed(4000 + rank)
+    for n_req in (0, 1, 5000 + 777 * rank):
+        qe = torch.randint(0, N, (n_req,), generator=gq).to(dev)
+        assert torch.equal(fsm.get_feature_exchange(qe).cpu(), feat[qe.cpu()])
+    qe = (torch.randint(0, N // world - 1, (3000,), generator=gq) * world + (world - 1)).to(dev)
+    assert torch.equal(fsm.get_feature_exchange(qe).cpu(), feat[qe.cpu()])
+    assert torch.equal(fsm.get_feature_exchange(qe), fsm._CAPI_get_feature(qe))
     # one-call loader over the sharded sampler + feature server == the separate plugin calls
     smp = dgs.classes.P2PCacheSampler.from_device_shards(sp, si, None, nids, N, rank)
     loader = dgs.classes.BatchLoader(smp, fsm)

@@ -201,6 +201,38 @@ def test_extract_p2p_virtual_ranks_bit_exact(dgs, cuda, P, rank, algo):
     assert np.array_equal(t2n(out), t2n(feat)[t2n(q)])
 
 
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("P", [1, 2, 3, 8])
+def test_route_ids_and_virtual_exchange(dgs, cuda, idt, P):
+    """dgs_route_ids (request routing of the id-exchange extract, north star (4)): counts = requests
+    per owner, send_idx = slot numbers grouped by owner, inv = the exact inverse of the grouping -
+    and, with P virtual ranks on one GPU (shard r = rows r::P, the all-to-all done by slicing), the
+    routed requests reproduce the closed-form feature rows in request order.  Request counts
+    around the 2048-id CTA chunk."""
+    N, D = 50000, 6
+    feat = dgs_synth.make_features(N, D, device=cuda)
+    shards = [feat[r::P].contiguous() for r in range(P)]
+    g = torch.Generator().manual_seed(3 + P)
+    for n in (0, 1, 31, 2048, 2049, 100003):
+        q = torch.randint(0, N, (n,), generator=g).to(idt).to(cuda)
+        send_idx, inv, counts = dgs.ops.route_ids(q, P)
+        assert send_idx.dtype == idt and inv.dtype == idt and counts.dtype == torch.int64
+        c = counts.cpu()
+        assert torch.equal(c, torch.bincount((q % P).cpu().long(), minlength=P))
+        assert torch.equal(torch.sort(inv).values.long(), torch.arange(n, device=cuda))
+        assert torch.equal(send_idx[inv.long()], q // P)
+        owner_of_pos = torch.repeat_interleave(torch.arange(P), c).to(cuda)
+        assert torch.equal(owner_of_pos[inv.long()], (q % P).long())
+        # the owners' side: rows of their own shard, concatenated in send order; then request order
+        offs = [0] + torch.cumsum(c, 0).tolist()
+        rows = torch.cat([dgs.ops._CAPI_cuda_index_select(shards[d], send_idx[offs[d]:offs[d + 1]])
+                          for d in range(P)])
+        out = dgs.ops._CAPI_cuda_index_select(rows, inv)
+        assert torch.equal(out, dgs_synth.feature_rows(q.long(), D, torch.float32))
+    with pytest.raises(RuntimeError):
+        dgs.ops.route_ids(q, 0)
+
+
 def test_feature_server_reference_test_input(dgs, cuda):
     """tests/test_feature_server.py:20-52 with one rank (cache [0, 3], misses from pinned host)."""
     feature = torch.arange(0, 100, 1).float().pin_memory().reshape(10, 10)
@@ -1327,24 +1359,38 @@ def test_pin_memory_roundtrip(dgs, cuda):
 
 
 # ------------------------------------------------------------------ full-size properties
-def test_full_size_products_properties(dgs, cuda):
+# BASELINE configs at (or scaled to) their shape: (nodes, edges, feature dim, dtype, batch, fan-out).
+# products is configs[1] at full size; the papers100M / friendster cases keep the config's row
+# format (128 x fp32 / 256 x bf16 = 512-byte rows), mean degree, batch and fan-out - so they take
+# the same kernels (friendster: Floyd in 32 registers for k = 20, one kernel per phase for the 14 M
+# padded slots of the last hop, the warp-autonomous gather) - on 1/32 resp. 1/16 of the nodes, which
+# is what fits next to torch's checking code on one GPU in seconds.
+_SHAPE_CASES = {
+    "products": dgs_synth.SHAPES["products"] + (1024, [15, 10, 5]),
+    "papers100M/32": (111_059_956 // 32, 1_615_685_872 // 32, 128, torch.float32, 1024, [15, 10, 5]),
+    "friendster/16": (65_608_366 // 16, 1_806_067_135 // 16, 256, torch.bfloat16, 4096, [20, 15, 10]),
+}
+
+
+@pytest.mark.parametrize("case", list(_SHAPE_CASES))
+def test_full_size_products_properties(dgs, cuda, case):
     """BASELINE configs[1] at full size (2.45 M nodes, ~61 M edges, 100-dim fp32, batch 1024,
-    [15,10,5]) - too large for the CPU oracle, so size-independent properties are checked on the GPU
+    [15,10,5]) and configs 4 / 5 in their row format, batch and fan-out (_SHAPE_CASES) - too large
+    for the CPU oracle, so size-independent properties are checked on the GPU
     with torch ops: every sampled (row, col) is an edge of the graph, per-seed counts are
     min(deg, k), no neighbour position is taken twice, the frontier is the first-occurrence unique
     of cat(seeds, cols), relabelled ids invert through the frontier, extract composes
     (gather(gather(T, p), q) == gather(T, p[q])) and reproduces the closed-form feature rows."""
-    N, E, D, dt = dgs_synth.SHAPES["products"]
+    N, E, D, dt, batch, fan = _SHAPE_CASES[case]
     indptr, indices, _ = dgs_synth.make_csr(N, E, device=cuda)
     feat = dgs_synth.make_features(N, D, dt, device=cuda)
     smp = dgs.classes.CSRSampler(indptr, indices)
-    seeds = dgs_synth.seed_batches(N, 1024, 1, seed=7, device=cuda)[0]
-    fan = [15, 10, 5]
+    seeds = dgs_synth.seed_batches(N, batch, 1, seed=7, device=cuda)[0]
     out = smp._CAPI_sample_node_classifiction(seeds, fan, False, rng_seed=99)
     cur = seeds
     # edge keys of the whole graph, sorted once: (src << 32) | dst  (N < 2^31)
     deg_all = indptr[1:] - indptr[:-1]
-    for (s_, f_, r_, c_), k in zip(out, (5, 10, 15)):
+    for (s_, f_, r_, c_), k in zip(out, fan[::-1]):
         assert torch.equal(s_, cur)
         deg = deg_all[cur]
         cnt = torch.clamp(deg, max=k)

@@ -9,7 +9,7 @@ import torch.multiprocessing as mp
 
 import dgs_synth
 from DistGNN.dataloading import SeedGenerator
-from DistGNN.dist import create_communicator, owner_of, partition_seeds
+from DistGNN.dist import create_communicator, exchange_extract, owner_of, partition_seeds
 
 
 def test_seed_generator_matches_reference_semantics():
@@ -141,6 +141,19 @@ def _free_port():
     return p
 
 
+def _route_torch(nids, world):
+    """What dgs_route_ids computes, restated with torch ops (test double for the gloo run)."""
+    owner = nids % world
+    order = torch.argsort(owner, stable=True)
+    inv = torch.empty_like(nids)
+    inv[order] = torch.arange(nids.numel(), dtype=nids.dtype)
+    return (nids // world)[order], inv, torch.bincount(owner, minlength=world)
+
+
+def _gather_torch(table, idx):
+    return table[idx.long()]
+
+
 def _worker(rank, world, port, out):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
@@ -176,6 +189,18 @@ def _worker(rank, world, port, out):
         sizes = [None] * world
         dist.all_gather_object(sizes, mine.tolist())
         assert sorted(sum(sizes, [])) == list(range(101))
+        # (5) id-exchange extract (north star (4)): ids to the owners, rows back, request order
+        # restored - the collective logic with torch restatements of the two native kernels
+        # (dgs.ops.route_ids / _CAPI_cuda_index_select), on this rank's modulo shard
+        D = 5
+        local_rows = dgs_synth.make_features(N, D, nids=nids)
+        g = torch.Generator().manual_seed(100 + rank)
+        for n_req in (0, 1, 257 + 13 * rank):
+            req = torch.randint(0, N, (n_req,), generator=g)
+            got = exchange_extract(req, world, rank, local_rows, route=_route_torch, gather=_gather_torch)
+            assert got.shape == (n_req, D) and torch.equal(got, dgs_synth.feature_rows(req, D, torch.float32))
+        with pytest.raises(RuntimeError):
+            exchange_extract(req, world + 1, rank, local_rows, route=_route_torch, gather=_gather_torch)
         out.put((rank, "ok"))
     except BaseException as e:  # noqa: BLE001
         out.put((rank, repr(e)))
