@@ -74,13 +74,14 @@ constexpr int kGatherUnroll = 4;
 template <typename IdT, typename VecT>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_rows_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, int64_t row_bytes,
-                   uint32_t vpr /* vectors per row */, uint32_t vpr_magic, char *__restrict__ out) {
+                   uint32_t vpr /* vectors per row */, uint32_t vpr_magic, char *__restrict__ out,
+                   int tile_rows /* <= kGatherRows */) {
   __shared__ const char *s_src[kGatherRows];
   if (src.n_dev != nullptr) n = min(n, (int64_t)*src.n_dev);
-  const int64_t num_tiles = (n + kGatherRows - 1) / kGatherRows;
+  const int64_t num_tiles = (n + tile_rows - 1) / tile_rows;
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kGatherRows;
-    const int rows = (int)min((int64_t)kGatherRows, n - row0);
+    const int64_t row0 = tile * tile_rows;
+    const int rows = (int)min((int64_t)tile_rows, n - row0);
     __syncthreads();  // previous tile's readers are done with s_src
     if (threadIdx.x < rows) {
       IdT nid = nids[row0 + threadIdx.x];
@@ -374,6 +375,7 @@ gather_rows_tma_kernel(RowSource src, const IdT *__restrict__ nids, int64_t n, i
 // gather next to another kernel on a second stream (BatchLoader.iter_many) lowers it so that the
 // other kernel finds room: an NVLink-bound gather needs ~2 CTAs per SM to keep the link busy.
 static int g_gather_ctas_per_sm = 8;
+static int g_gather_tile_rows = 0;   // 0 = kGatherRows (tuning knob, dgs_set_gather_tile_rows)
 
 static inline uint32_t div_magic(uint32_t d) { return (uint32_t)(((1ull << 32) + d - 1) / d); }
 
@@ -443,31 +445,32 @@ static int launch_gather(const RowSource &src, const IdT *nids, int64_t n, int64
     DGS_LAUNCH_CHECK();
     return 0;
   }
-  int grid = grid_for(n, kGatherRows, g_gather_ctas_per_sm);
+  const int tile_rows = (g_gather_tile_rows >= 1 && g_gather_tile_rows <= kGatherRows) ? g_gather_tile_rows : kGatherRows;
+  int grid = grid_for(n, tile_rows, g_gather_ctas_per_sm);
   if (all_aligned16 && row_bytes % 16 == 0) {
     uint32_t vpr = (uint32_t)(row_bytes / 16);
     DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large for the "
                 "tile index math (max %d)", (long long)row_bytes, 65535 / kGatherRows * 16);
     gather_rows_kernel<IdT, int4><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
-                                                                   div_magic(vpr), out);
+                                                                   div_magic(vpr), out, tile_rows);
   } else if (row_bytes % 8 == 0) {
     uint32_t vpr = (uint32_t)(row_bytes / 8);
     DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
                 (long long)row_bytes);
     gather_rows_kernel<IdT, int2><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
-                                                                   div_magic(vpr), out);
+                                                                   div_magic(vpr), out, tile_rows);
   } else if (row_bytes % 4 == 0) {
     uint32_t vpr = (uint32_t)(row_bytes / 4);
     DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
                 (long long)row_bytes);
     gather_rows_kernel<IdT, int><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
-                                                                  div_magic(vpr), out);
+                                                                  div_magic(vpr), out, tile_rows);
   } else {
     uint32_t vpr = (uint32_t)row_bytes;
     DGS_REQUIRE((uint64_t)vpr * kGatherRows < 65536, "extract: row_bytes %lld too large",
                 (long long)row_bytes);
     gather_rows_kernel<IdT, char><<<grid, kGatherThreads, 0, st>>>(src, nids, n, row_bytes, vpr,
-                                                                   div_magic(vpr), out);
+                                                                   div_magic(vpr), out, tile_rows);
   }
   DGS_LAUNCH_CHECK();
   return 0;
@@ -482,6 +485,12 @@ using namespace dgsb;
 extern "C" int dgs_set_gather_ctas_per_sm(int ctas) {
   DGS_REQUIRE(ctas >= 1 && ctas <= 8, "dgs_set_gather_ctas_per_sm: 1..8");
   g_gather_ctas_per_sm = ctas;
+  return 0;
+}
+
+extern "C" int dgs_set_gather_tile_rows(int rows) {
+  DGS_REQUIRE(rows >= 0 && rows <= kGatherRows, "dgs_set_gather_tile_rows: 0 (default) .. %d", kGatherRows);
+  g_gather_tile_rows = rows;
   return 0;
 }
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "dgs_loc_table_unpack": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "dgs_index_select": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "dgs_set_gather_ctas_per_sm": (C.c_int, [C.c_int]),
+    "dgs_set_gather_tile_rows": (C.c_int, [C.c_int]),
     "dgs_extract_p2p": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp,
                                   C.c_int, c_vp]),
     "dgs_extract_sharded": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),

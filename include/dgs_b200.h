@@ -126,6 +126,8 @@ int dgs_index_select(const void *table, int64_t row_bytes, int itype, const void
 /* Tuning knob (process-wide, default 8): resident CTAs per SM the gather kernels size their grid
  * for.  Lower it when a gather shares the GPU with another kernel on a second stream. */
 int dgs_set_gather_ctas_per_sm(int ctas);
+/* Tuning knob (process-wide): rows per CTA tile of the algo-1 gather, 1..64; 0 = default (64). */
+int dgs_set_gather_tile_rows(int rows);
 /* cached gather: row i comes from peer shard feat[dev][idx] when nids[i] hits the location
  * table, else from host_table[nids[i]] (pinned / registered host memory, may be NULL when every
  * id is cached). */
