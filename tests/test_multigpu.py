@@ -1,5 +1,5 @@
-"""GPU (>= 2 devices): the collective build path (NCCL id exchange, CUDA-IPC shard mapping) and
-in-kernel peer loads, on the reference's 2-rank scenarios and a sharded parity check."""
+"""GPU (>= 2 devices): the collective build path (NCCL id exchange, VMM shard mapping with the
+legacy CUDA-IPC fallback), in-kernel peer loads and the NCCL id-exchange extract, on the reference's 2-rank scenarios and a sharded parity check."""
 import os
 import subprocess
 import sys
