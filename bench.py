@@ -879,9 +879,12 @@ def run_b200(args, fan_out):
         "e2e_fused": {"value": t_fused["edges"] / (t_fused["ms"] * 1e-3), "unit": UNIT,
                       "ms_per_step": t_fused["ms"] / K,
                       "batches_per_sec": world * K / (t_fused["ms"] * 1e-3),
-                      "note": "extension, not the reference-facing API: dgs.classes.BatchLoader enqueues "
-                              "sample -> extract (frontier size read on the device) -> labels and "
-                              "syncs once; same inputs, outputs and copies as e2e"},
+                      "note": "extension, not the reference-facing API: dgs.classes.BatchLoader.load = one "
+                              "native call: seeds H2D -> labels + D2H -> sample -> extract (frontier size "
+                              "read on the device); returns when the hop sizes and the labels are on the "
+                              "host, WITHOUT draining the stream (the extract of step i overlaps the host "
+                              "side of step i + 1; everything is synchronised at the end of the K steps); "
+                              "same inputs, outputs and copies as e2e"},
         "e2e_pipelined": pipelined,
         "gpu_launches": launches,
         "roofline": dominant,

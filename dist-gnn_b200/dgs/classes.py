@@ -1067,8 +1067,9 @@ class BatchLoader:
     def load(self, seeds, fan_out, replace=False, rng_seed=None, algo=0, labels_out=None):
         """-> (blocks, features of blocks[-1][1], labels of seeds or None).  `labels_out` (pinned host
         tensor) additionally receives the labels inside the same host round trip.  One native call
-        (dgs_load_batch) enqueues seeds H2D -> sample -> extract -> labels (-> D2H) and waits for the
-        hop sizes."""
+        (dgs_load_batch) enqueues seeds H2D -> labels (-> D2H) -> sample -> extract and waits for the
+        hop sizes (and the labels' event).  The stream is not drained: blocks / features are
+        stream-ordered CUDA tensors like the result of any torch op, `labels_out` is host-valid."""
         l = lib()
         fan_out = [int(k) for k in fan_out]
         L = len(fan_out)

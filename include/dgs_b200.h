@@ -306,13 +306,14 @@ int dgs_sample_blocks_multi(const dgs_graph_t *g, int num_batches, const void *s
  * One call per mini-batch = the caller loop of example/graphsage/node_classification.py:219-230
  * (sampler._CAPI_sample_node_classifiction, feature_server._CAPI_get_feature, label index_select)
  * enqueued back to back with ONE host round trip: seeds H2D (when seeds_on_host: `seeds` is pinned
- * host memory, seeds_dev a device staging buffer of num_seeds ids) -> dgs_sample_blocks_enqueue ->
- * dgs_extract_dyn of the input frontier (size read on the device; x_out holds x_rows_ub rows) ->
- * label gather into labels_out_dev (+ D2H into pinned labels_out_host).  Outputs: `arena` (ids) holds
- * hop l's frontier / row / col at hop_offsets[3 l .. 3 l + 2] (elements) and the 2 L int64 hop sizes
- * at counts_offset (elements); the sizes are also in counts_host (pinned) when the call returns.
- * With labels_out_host the call returns after the stream has drained, else right after the sizes
- * arrived (extract / label kernels may still be running, ordered on `stream`).  If the frontier
+ * host memory, seeds_dev a device staging buffer of num_seeds ids) -> label gather into
+ * labels_out_dev (+ D2H into pinned labels_out_host; the labels depend on the seeds only, so they go
+ * first) -> dgs_sample_blocks_enqueue -> dgs_extract_dyn of the input frontier (size read on the
+ * device; x_out holds x_rows_ub rows).  Outputs: `arena` (ids) holds hop l's frontier / row / col at
+ * hop_offsets[3 l .. 3 l + 2] (elements) and the 2 L int64 hop sizes at counts_offset (elements).
+ * Valid on the host when the call returns: the sizes in counts_host (pinned) and labels_out_host
+ * (waited for through an event).  The call does NOT drain the stream: the last emit phase and the
+ * extract may still be running, ordered on `stream` like the result of any CUDA op.  If the frontier
  * turned out larger than x_rows_ub (the caller's bound) only x_rows_ub rows were gathered. */
 typedef struct {
   const void *table;            /* plain table (device / pinned host), or the pinned-host fallback of a
