@@ -1,5 +1,4 @@
 """NCCL bootstrap for the data-path plugin (python/DistGNN/dist/communicator.py:5-17)."""
-import torch
 import torch.distributed as dist
 
 
