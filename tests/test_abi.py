@@ -113,6 +113,19 @@ def test_batch_workspace_planning_without_gpu():
                             None, 0, 0, None, None, 0, None, None, 0, None)
     assert rc != 0 and b"null argument" in lib.dgs_last_error()
     assert lib.dgs_set_gather_ctas_per_sm(0) != 0 and lib.dgs_set_gather_ctas_per_sm(8) == 0
+    assert lib.dgs_set_gather_tile_rows(65) != 0 and lib.dgs_set_gather_tile_rows(-1) != 0
+    assert lib.dgs_set_gather_tile_rows(32) == 0 and lib.dgs_set_gather_tile_rows(0) == 0
+    # request routing of the id-exchange extract: one 4-byte counter per (owner, 2048-id chunk);
+    # bad arguments are refused before anything is launched
+    assert lib.dgs_route_ws_bytes(0, 8) == 8 * 4 and lib.dgs_route_ws_bytes(2048, 8) == 8 * 4
+    assert lib.dgs_route_ws_bytes(2049, 3) == 2 * 3 * 4
+    assert lib.dgs_route_ws_bytes(100, 0) == -1 and lib.dgs_route_ws_bytes(100, 17) == -1
+    assert lib.dgs_route_ws_bytes(-1, 2) == -1
+    a = C.addressof(buf)
+    assert lib.dgs_route_ids(1, a, 10, 0, a, a, a, a, 64, None) != 0 and b"world" in lib.dgs_last_error()
+    assert lib.dgs_route_ids(1, a, 10, 2, a, a, None, a, 64, None) != 0 and b"null" in lib.dgs_last_error()
+    assert lib.dgs_route_ids(1, a, 100000, 2, a, a, a, a, 64, None) != 0 and b"workspace" in lib.dgs_last_error()
+    assert lib.dgs_route_ids(0, a, 1 << 31, 2, a, a, a, a, 1 << 40, None) != 0 and b"int32" in lib.dgs_last_error()
     assert lib.dgs_launch_count() == before
 
 
