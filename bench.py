@@ -83,6 +83,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-extra-layout", action="store_true")
+    ap.add_argument("--nvtx", action="store_true",
+                    help="wrap the step's two plugin calls in the reference's NVTX ranges "
+                         "('sampling', 'loading') for ncu --nvtx-include")
     ap.add_argument("--no-exchange", action="store_true",
                     help="N > 1: skip the NCCL id-exchange variant in the extract-only leg")
     args = ap.parse_args()
@@ -543,9 +546,20 @@ def run_b200(args, fan_out):
     seeds_dev = seeds_all.to(dev)
     seeds_pin = seeds_all.pin_memory()
 
+    if args.nvtx:
+        # the reference's ranges (scripts/ncu_sampling.py:38,48, scripts/ncu_feature.py:17-20), for
+        #   ncu --nvtx --nvtx-include "sampling/" ... / --nvtx-include "loading/" ...
+        rng_push, rng_pop = torch.cuda.nvtx.range_push, torch.cuda.nvtx.range_pop
+    else:
+        rng_push = rng_pop = lambda *a: None
+
     def step_device(i):
+        rng_push("sampling")
         blocks = sampler._CAPI_sample_node_classifiction(seeds_dev[i], fan_out, False)
+        rng_pop()
+        rng_push("loading")
         x = extract(blocks[-1][1])
+        rng_pop()
         return blocks, x
 
     lab_host = torch.empty(args.batch, dtype=torch.int64).pin_memory()
