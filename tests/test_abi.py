@@ -16,6 +16,19 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(dgs_[a-z0-9_]+)\s*\(", src)))
 
 
+def test_header_is_plain_c_and_cxx():
+    """The drop-in boundary must be consumable from C (cgo / JNI style FFI) and C++ (the reference's
+    pybind module): include/dgs_b200.h compiles stand-alone in both languages."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    for cc, lang, std in (("gcc", "c", "-std=c11"), ("g++", "c++", "-std=c++17")):
+        p = subprocess.run([cc, std, "-Wall", "-Werror", "-fsyntax-only", "-x", lang, HEADER],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+
+
 def test_header_symbols_exported():
     from dgs import _lib
     lib = _lib.lib()
