@@ -568,6 +568,76 @@ def test_biased_without_replacement_exact_topk(dgs, cuda, k):
         cur = f
 
 
+@pytest.mark.parametrize("k", [10, 25, 40])
+def test_biased_zero_weight_edges_exact(dgs, cuda, k):
+    """Zero-weight edges (key u^(1/0) = 0 in rowwise_sampling_bias.cu:112-113 - an edge
+    of weight 0 is selectable only when fewer than k positive-weight edges exist).  Here the key of
+    such an edge is -inf and ties go to the smaller position, so the sample is still EXACTLY the
+    stable top-k of the keys for k <= 32: rows with fewer positive weights than k (every positive
+    edge first, then the lowest zero-weight positions), with more than k (no zero-weight edge ever),
+    all-zero rows, positives only at the very end of a multi-chunk row - through the one-pass,
+    multi-pass and hub paths of the per-hop op and of the batch kernel; the k = 40 reservoir (beyond
+    the reference's k <= 32) must pick exactly the top positive keys and fill up with zero-weight
+    edges of its choice.  With replacement a zero-weight edge is never drawn."""
+    N = 30000
+    indptr, indices, w, special = _ares_graph(N, seed=3)
+    keep = {11: [2, 17, 39], 12: [0, 100, 255, 256, 512], 13: list(range(0, 2000, 10)), 14: [5, 4095, 4096, 8191, 12000, 16384, 19999],
+            15: list(range(500, 512)), 16: [], 17: [32], 18: list(range(4087, 4097))}
+    for n, pos in keep.items():
+        b, e = int(indptr[n]), int(indptr[n + 1])
+        ww = torch.zeros(e - b)
+        ww[pos] = w[b:e][pos]
+        w[b:e] = ww
+    # ordinary rows: a third of all weights are zero
+    g = torch.Generator().manual_seed(40 + k)
+    mask = torch.rand(w.numel(), generator=g) < 0.33
+    lo = int(indptr[100])
+    w[lo:][mask[lo:]] = 0.0
+    ip, ix, wd = indptr.to(cuda), indices.to(cuda), w.to(cuda)
+    others = torch.randperm(N - 100, generator=g)[:500] + 100
+    seeds = torch.cat([torch.tensor(special), others])
+    seeds = seeds[torch.randperm(seeds.numel(), generator=g)]
+    R = 0x7654321 + k
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(seeds.to(cuda), ip, ix, wd, k, False, rng_seed=R)
+    cnt = torch.clamp(indptr[seeds + 1] - indptr[seeds], max=k)
+    per_seed = torch.split(col.cpu(), cnt.tolist())
+    assert torch.equal(row.cpu(), torch.repeat_interleave(seeds, cnt))
+
+    def check(per_seed, key):
+        if k <= 32:      # descending key order, ties (the -inf keys) by position: exact
+            _check_ares_hop(dgs, wd, indptr, N, seeds.tolist(), per_seed, k, key, ordered=True)
+        for i, (nid, got) in enumerate(zip(seeds.tolist(), per_seed)):
+            b, e = int(indptr[nid]), int(indptr[nid + 1])
+            if e - b <= k:
+                assert ((got - nid * 1009) % N).tolist() == list(range(e - b))
+                continue
+            # the property the reference states, independent of tie-breaking (the k > 32 reservoir
+            # may keep ANY zero-weight edges): positives first, and exactly the top positive keys
+            pos = ((got - nid * 1009) % N).tolist()
+            assert len(set(pos)) == k and all(0 <= t < e - b for t in pos)
+            wrow = w[b:e]
+            npos = int((wrow > 0).sum())
+            picked = sorted(t for t in pos if wrow[t] > 0)
+            assert len(picked) == min(npos, k), (nid, npos, len(picked))
+            exp = _expected_ares(dgs, wd, indptr, nid, k, key, i).tolist()
+            assert picked == sorted(t for t in exp if wrow[t] > 0), (nid, e - b, k)
+
+    check(per_seed, R)
+    # batch kernel (hub rows deferred to the chunked hub phase), first hop checked exactly
+    smp = dgs.classes.CSRSampler(ip, ix, wd)
+    out = smp._pipe.sample(seeds.to(cuda), [5, k], False, R)
+    s_, f_, r_, c_ = out[0]
+    per_seed = torch.split(f_.cpu()[c_.cpu()], cnt.tolist())
+    check(per_seed, (R + GOLDEN) & M64)
+    # with replacement: never a zero-weight edge (rows with at least one positive weight)
+    has_pos = torch.tensor([bool((w[int(indptr[n]):int(indptr[n + 1])] > 0).any()) for n in seeds.tolist()])
+    sd = seeds[has_pos]
+    row, col = dgs.ops._CAPI_cuda_sample_neighbors_bias(sd.to(cuda), ip, ix, wd, k, True, rng_seed=R)
+    rowc, colc = row.cpu(), col.cpu()
+    t = (colc - rowc * 1009) % N
+    assert bool((w[indptr[rowc] + t] > 0).all())
+
+
 @pytest.mark.parametrize("case", ["many_hubs", "huge_row"])
 def test_biased_hub_phase_fallbacks_exact(dgs, cuda, case):
     """The chunked hub phase of the batch kernel has static limits (1024 deferred rows, 32 chunks of
