@@ -195,7 +195,7 @@ def _worker(rank, world, port, out):
         D = 5
         local_rows = dgs_synth.make_features(N, D, nids=nids)
         g = torch.Generator().manual_seed(100 + rank)
-        for n_req in (0, 1, 257 + 13 * rank):
+        for n_req in (0, 1, 257 + 13 * rank, 0 if rank == 0 else 50, 64 if rank == 0 else 0):
             req = torch.randint(0, N, (n_req,), generator=g)
             got = exchange_extract(req, world, rank, local_rows, route=_route_torch, gather=_gather_torch)
             assert got.shape == (n_req, D) and torch.equal(got, dgs_synth.feature_rows(req, D, torch.float32))
